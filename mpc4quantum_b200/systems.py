@@ -1,0 +1,234 @@
+"""Benchmark systems and ensemble draws, stated with plain numpy (no qutip).
+
+Specification source: the reference's test utilities and state-preparation tests
+(/root/reference/tests/util_qubits.py:19-138, tests/test_mpc4quantum.py:281-368, 504-564, 607-670)
+and the ensemble definitions of SURVEY.md section 8(d).  These are *inputs*: host-side, built once.
+"""
+import numpy as np
+
+from .experiment import QExperiment, QCoupledExperiment, QExperiment32, EnsembleQExperiment
+from .model import DMDc
+from .mpc import StepClock
+from .vectorize import discretize_homogeneous, liouvillian
+
+SX = np.array([[0, 1], [1, 0]], dtype=complex)
+SY = np.array([[0, -1j], [1j, 0]], dtype=complex)
+SZ = np.array([[1, 0], [0, -1]], dtype=complex)
+I2 = np.eye(2, dtype=complex)
+
+
+def rx(phi):
+    """Single-qubit x rotation exp(-i phi sx / 2) (qutip.qip.operations.rx)."""
+    c, s = np.cos(phi / 2), np.sin(phi / 2)
+    return np.array([[c, -1j * s], [-1j * s, c]], dtype=complex)
+
+
+def proj(d, k):
+    out = np.zeros((d, d), dtype=complex)
+    out[k, k] = 1
+    return out
+
+
+def destroy(d):
+    return np.diag(np.sqrt(np.arange(1, d)), 1).astype(complex)
+
+
+class RWA_Qubit:
+    """tests/util_qubits.py:60-80: H0 = (wQ - wR)/2 sz, H1 = sx/2."""
+
+    def __init__(self, wQ, wD, wR):
+        self.dim_s, self.dim_x, self.dim_u = 2, 4, 1
+        self._w0, self._wD, self._wR = wQ, wD, wR
+        H0 = 0.5 * (wQ - wR) * SZ
+        H1 = 0.5 * SX
+        self.H_list = [H0, H1]
+        self.QE = QExperiment(H0, [H1])
+
+
+class RWA_Transmon:
+    """tests/util_qubits.py:92-111: H0 = alpha |2><2|, HX = (a^+ + a)/2, HY = i (a^+ - a)/2."""
+    _QE = QExperiment
+
+    def __init__(self, alpha):
+        self.dim_s, self.dim_x, self.dim_u = 3, 9, 2
+        self._delta = alpha
+        a = destroy(3)
+        H0 = alpha * proj(3, 2)
+        HX = 0.5 * (a.conj().T + a)
+        HY = 0.5j * (a.conj().T - a)
+        self.H_list = [H0, HX, HY]
+        self.QE = self._QE(H0, [HX, HY])
+
+
+class RWA_Transmon_Reduced(RWA_Transmon):
+    """tests/util_qubits.py:119-138: same plant, observed only in the qubit block."""
+    _QE = QExperiment32
+
+
+class RWA_Crosstalk:
+    """tests/util_qubits.py:39-57: H0 = xi/2 sz(x)sz; H1 = [sx(x)I / 2, I(x)sy / 2]."""
+
+    def __init__(self, crosstalk):
+        self.dim_u, self.dim_s, self.dim_x = 2, 4, 16
+        self.crosstalk = crosstalk
+        H0 = 0.5 * crosstalk * np.kron(SZ, SZ)
+        H_x1 = 0.5 * np.kron(SX, I2)
+        H_x2 = 0.5 * np.kron(I2, SY)
+        self.H_list = [H0, H_x1, H_x2]
+        self.H_list_1 = [0 * I2, SX]
+        self.H_list_2 = [0 * I2, SY]
+        self.QE = QCoupledExperiment(H0, [H_x1, H_x2])
+
+
+class RWA_Coupled:
+    """tests/util_qubits.py:19-36: H0 = sz(x)sz; controls sy(x)I, I(x)sy, sz(x)I."""
+
+    def __init__(self):
+        self.dim_u, self.dim_s, self.dim_x = 3, 4, 16
+        self.H_list = [np.kron(SZ, SZ), np.kron(SY, I2), np.kron(I2, SY), np.kron(SZ, I2)]
+        self.QE = QExperiment(self.H_list[0], self.H_list[1:])
+
+
+def _pack(**kw):
+    return kw
+
+
+def config_qubit(order=1):
+    """BASELINE config 1 (tests/test_mpc4quantum.py:607-670): ideal qubit |0> -> |1>, 1 % detuned plant."""
+    clock = StepClock(dt=1, horizon=10, n_steps=20)
+    sat = 2 * np.pi * 0.1
+    du = 0.5 * sat
+    wq = 2 * np.pi * 4
+    nominal = RWA_Qubit(wq, wq, wq)
+    A_init = discretize_homogeneous([liouvillian(h) for h in nominal.H_list], clock.dt, order)
+    plant = RWA_Qubit(wq * 0.99, wq, wq)
+    Q = np.diag([1.0, 0, 0, 1.0])
+    R = (1e-2 / sat ** 2) * np.eye(1)
+    Rx = rx(1e-4)
+    rho0 = Rx @ proj(2, 0) @ Rx.conj().T
+    target = proj(2, 1).reshape(-1)
+    S, H = clock.n_steps, clock.horizon
+    return _pack(name='qubit', x0=rho0.reshape(-1), dim_u=1, order=order,
+                 X_targ=np.tile(target[:, None], (1, S + H + 1)), U_targ=np.zeros((1, S + H)),
+                 clock=clock, experiment=plant.QE, model=_dmdc(A_init, 4), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=True, target=target, wq=wq, nominal=nominal)
+
+
+def config_transmon(order=1, horizon=16, n_steps=20):
+    """BASELINE config 3 (tests/test_mpc4quantum.py:504-564): 3-level transmon, DRAG-like state transfer."""
+    clock = StepClock(dt=0.25, horizon=horizon, n_steps=n_steps)
+    sat = 2 * np.pi * 0.25
+    du = 0.5 * sat
+    anharm = -2 * np.pi * 0.1 * (1 / clock.dt)
+    qubit = RWA_Transmon(alpha=anharm)
+    A_init = discretize_homogeneous([liouvillian(h) for h in qubit.H_list], clock.dt, order)
+    Q = np.zeros((9, 9))
+    Q[0, 0] = 1
+    Q[4, 4] = 1
+    R = (1e-3 / sat ** 2) * np.eye(2)
+    Rx = rx(1e-4)
+    rho0 = proj(3, 0)
+    rho0[:2, :2] = Rx.conj().T @ rho0[:2, :2] @ Rx
+    target = proj(3, 1).reshape(-1)
+    S, H = clock.n_steps, clock.horizon
+    return _pack(name='transmon', x0=rho0.reshape(-1), dim_u=2, order=order,
+                 X_targ=np.tile(target[:, None], (1, S + H + 1)), U_targ=np.zeros((2, S + H)),
+                 clock=clock, experiment=qubit.QE, model=_dmdc(A_init, 9), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=True, target=target, anharm=anharm, nominal=qubit)
+
+
+def config_crosstalk(crosstalk=0.0, wiring='consistent'):
+    """BASELINE config 4 (tests/test_mpc4quantum.py:281-368): two qubits, stacked 8-dim model, 16-dim plant.
+
+    The reference test wires the model and the plant inconsistently: the model's first
+    control drives qubit 2 with sy and omits the 1/2.  ``wiring='consistent'`` (default) builds the model from
+    the plant's own single-qubit generators (u0 -> sx/2 on qubit A, u1 -> sy/2 on qubit B);
+    ``wiring='reference'`` reproduces the test literally.
+    """
+    clock = StepClock(dt=0.5, horizon=20, n_steps=50)
+    clock.measure_freq = 2
+    sat = 2 * np.pi * 0.1
+    du = 0.25
+    qubits = RWA_Crosstalk(crosstalk)
+    Z4 = np.zeros((4, 4), dtype=complex)
+
+    def blk(a, b):
+        return np.block([[a, Z4], [Z4, b]])
+    if wiring == 'reference':
+        L1 = [liouvillian(h) for h in qubits.H_list_1]
+        L2 = [liouvillian(h) for h in qubits.H_list_2]
+        A_cts = [blk(L1[0], L2[0]), blk(Z4, L2[1]), blk(L1[1], Z4)]
+    else:
+        A_cts = [blk(Z4, Z4), blk(liouvillian(0.5 * SX), Z4), blk(Z4, liouvillian(0.5 * SY))]
+    A_dst = discretize_homogeneous(A_cts, clock.dt, 1)
+    r1, r2 = rx(-1e-3), rx(1e-3)
+    rho1_init = r1 @ proj(2, 0) @ r1.conj().T
+    rho2_init = r2 @ proj(2, 0) @ r2.conj().T
+    x0 = np.kron(rho1_init, rho2_init).reshape(-1)
+    target_model = np.concatenate([proj(2, 1).reshape(-1), proj(2, 0).reshape(-1)])
+    target_plant = np.kron(proj(2, 1), proj(2, 0)).reshape(-1)
+    q = np.diag([1.0, 0, 0, 1.0])
+    Q = np.block([[q, np.zeros((4, 4))], [np.zeros((4, 4)), q]])
+    R = 1e-3 * np.eye(2)
+    S, H = clock.n_steps, clock.horizon
+    return _pack(name='crosstalk', x0=x0, dim_u=2, order=1,
+                 X_targ=np.tile(target_model[:, None], (1, S + H + 1)), U_targ=np.zeros((2, S + H)),
+                 clock=clock, experiment=qubits.QE, model=_dmdc(A_dst, 8), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=False, target=target_plant, nominal=qubits)
+
+
+def _dmdc(A_full, c):
+    p = A_full.shape[1] // c - 1
+    return DMDc(c, c, c * p, A_full)
+
+
+def mpc_args(cfg):
+    """Positional/keyword arguments for mpc()/mpc_ensemble() from a config dict."""
+    args = (cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'],
+            cfg['experiment'], cfg['model'], cfg['Q'], cfg['R'], cfg['Qf'])
+    kw = dict(sat=cfg['sat'], du=cfg['du'], warm_start=cfg['warm_start'], progress_bar=False)
+    return args, kw
+
+
+# ----------------------------------------------------------------------------
+# Ensembles of perturbed plants; drawn on the host from a fixed seed so that the
+# members are independent of the GPU count.  Returned arrays: H0 [N, d, d], H1 [N, m, d, d] complex128.
+# ----------------------------------------------------------------------------
+ENSEMBLE_SEED = 20220113
+
+
+def ensemble_qubit(N, seed=ENSEMBLE_SEED, wq=2 * np.pi * 4):
+    """C2: detuning scale s ~ U[0.98, 1.02] (plant H0 = (s-1) wq sz / 2), amplitude scale a ~ U[0.9, 1.1]."""
+    rng = np.random.default_rng(seed)
+    s = rng.uniform(0.98, 1.02, N)
+    a = rng.uniform(0.9, 1.1, N)
+    H0 = 0.5 * ((s - 1) * wq)[:, None, None] * SZ
+    H1 = (a[:, None, None] * (0.5 * SX))[:, None]
+    return EnsembleQExperiment(H0, H1), dict(detuning_scale=s, amplitude_scale=a)
+
+
+def ensemble_transmon(N, seed=ENSEMBLE_SEED, dt=0.25):
+    """C3/C5: anharmonicity scale ~U[0.9,1.1], amplitude scale ~U[0.9,1.1], detuning ~U[-0.02,0.02] 2pi/dt on a^+a."""
+    rng = np.random.default_rng(seed)
+    k = rng.uniform(0.9, 1.1, N)
+    a_s = rng.uniform(0.9, 1.1, N)
+    det = rng.uniform(-0.02, 0.02, N) * 2 * np.pi / dt
+    alpha = -2 * np.pi * 0.1 / dt
+    a = destroy(3)
+    num = a.conj().T @ a
+    HX = 0.5 * (a.conj().T + a)
+    HY = 0.5j * (a.conj().T - a)
+    H0 = (k * alpha)[:, None, None] * proj(3, 2) + det[:, None, None] * num
+    H1 = np.stack([a_s[:, None, None] * HX, a_s[:, None, None] * HY], axis=1)
+    return EnsembleQExperiment(H0, H1), dict(anharm_scale=k, amplitude_scale=a_s, detuning=det)
+
+
+def ensemble_crosstalk(N, seed=ENSEMBLE_SEED):
+    """C4: ZZ strength xi ~ U[0, 2pi 0.02], amplitude scale ~U[0.9,1.1]; plant observed through partial traces."""
+    rng = np.random.default_rng(seed)
+    xi = rng.uniform(0, 2 * np.pi * 0.02, N)
+    a_s = rng.uniform(0.9, 1.1, N)
+    H0 = 0.5 * xi[:, None, None] * np.kron(SZ, SZ)
+    H1 = np.stack([a_s[:, None, None] * (0.5 * np.kron(SX, I2)), a_s[:, None, None] * (0.5 * np.kron(I2, SY))],
+                  axis=1)
+    return EnsembleQExperiment(H0, H1, kind='coupled'), dict(xi=xi, amplitude_scale=a_s)
