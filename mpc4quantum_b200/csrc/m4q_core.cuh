@@ -1,0 +1,948 @@
+// Warp-level building blocks of the MPC hot path (sm_100a).  One warp owns one ensemble member; all per-member
+// state lives in a warp-private slab of shared memory, the model blocks / costs are CTA-shared and read-only.
+//
+// Reference semantics restated here (paths relative to the reference repository):
+//   linearize      mpc4quantum/linearize.py:37-70   (A_t never materialised: A_t = sum_k phi_k(u_t) * block_k)
+//   QP             mpc4quantum/optimize.py:12-60    (ADMM on the control box, Riccati inner solve, active-set polish)
+//   line search    mpc4quantum/mpc.py:101-125       (time-major metric paired with state-major vectors)
+//   plant          mpc4quantum/experiment.py:202-212 + mpc.py:256-260 (expm conjugation per segment)
+//   lift / proj    mpc4quantum/experiment.py:29-37, 225-235, 248-306
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace m4q {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAXBLK = 16;   // max monomial blocks (p + 1)
+
+__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int rup(int a, int b) { return cdiv(a, b) * b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Compile-time configuration for a (complex state dim, control dim) pair.
+// TR1 x TC1: register tile of W = P^T [A|B] (N x Q);  TR2 x TC2: register tile of [A|B]^T W (Q x Q).
+// ---------------------------------------------------------------------------------------------------------
+template <int C_, int M_> struct Tiles { static constexpr int TR1 = 2, TC1 = 4, TR2 = 4, TC2 = 4; };
+template <> struct Tiles<4, 1>  { static constexpr int TR1 = 2, TC1 = 3, TR2 = 3, TC2 = 3; };
+template <> struct Tiles<9, 2>  { static constexpr int TR1 = 3, TC1 = 4, TR2 = 4, TC2 = 4; };
+template <> struct Tiles<8, 2>  { static constexpr int TR1 = 2, TC1 = 5, TR2 = 4, TC2 = 4; };
+template <> struct Tiles<16, 3> { static constexpr int TR1 = 4, TC1 = 9, TR2 = 6, TC2 = 9; };
+
+template <int C_, int M_> struct Cfg {
+    static constexpr int C = C_, N = 2 * C_, M = M_, Q = N + M_;
+    using T = Tiles<C_, M_>;
+    static constexpr int TR1 = T::TR1, TC1 = T::TC1, TR2 = T::TR2, TC2 = T::TC2;
+    static_assert(N % TR1 == 0, "row tile of mm1 must divide N");
+    static constexpr int LD = rup(cmax(cmax(rup(Q, TC1), rup(Q, TR2)), rup(Q, TC2)), 2);
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-private slab (offsets in doubles).  H is a run-time value.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF> struct Slab {
+    double *P, *AB, *W, *T21, *S, *K, *B, *D, *Sinv, *dv, *kk, *phi, *Xg, *Ug, *Xo, *Uo, *z, *y, *x0, *va, *vb,
+        *lo0, *hi0, *xcur, *xmeas, *scr;
+    int *mask;
+
+    __host__ __device__ static int doubles(int H, int nblk, int dd) {
+        return layout(nullptr, nullptr, H, nblk, dd);
+    }
+    // dd = plant state length in complex numbers (d*d); scr holds 4 complex d x d matrices for expm
+    __host__ __device__ static int layout(Slab *s, double *base, int H, int nblk, int dd) {
+        constexpr int N = CF::N, M = CF::M, LD = CF::LD;
+        int o = 0;
+        auto take = [&](double **dst, int cnt) {
+            if (s) *dst = base + o;
+            o += rup(cnt, 2);
+        };
+        Slab dummy;
+        Slab *q = s ? s : &dummy;
+        take(&q->P, N * N);
+        take(&q->AB, N * LD);
+        take(&q->W, N * LD);
+        take(&q->T21, M * N);
+        take(&q->S, M * M);
+        take(&q->K, H * M * N);
+        take(&q->B, H * N * M);
+        take(&q->D, H * N);
+        take(&q->Sinv, H * M * M);
+        take(&q->dv, H * N);
+        take(&q->kk, H * M);
+        take(&q->phi, H * nblk);
+        take(&q->Xg, (H + 1) * N);
+        take(&q->Ug, H * M);
+        take(&q->Xo, (H + 1) * N);
+        take(&q->Uo, H * M);
+        take(&q->z, H * M);
+        take(&q->y, H * M);
+        take(&q->x0, N);
+        take(&q->va, N);
+        take(&q->vb, N);
+        take(&q->lo0, M);
+        take(&q->hi0, M);
+        take(&q->xcur, 2 * dd);
+        take(&q->xmeas, 2 * dd);
+        take(&q->scr, cmax(8 * dd, 4 * M * MAXBLK));
+        double *mk = nullptr;
+        take(&mk, cdiv(H * M, 2));
+        if (s) s->mask = reinterpret_cast<int *>(mk);
+        return o;
+    }
+    // the part that must survive between launches in host-stepped mode: Xg | Ug | z | y | xcur | xmeas
+    __host__ __device__ static int persistent_doubles(int H, int dd) {
+        return (H + 1) * CF::N + 3 * H * CF::M + 4 * dd;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Stage operator A_t = sum_k w_k(t) block_k.  Fused loop: blocks = shared model [A, N_1..N_p], w = monomials of
+// the guess control (held in slab.phi).  Stand-alone QP: one dense block per stage, w = 1.
+// ---------------------------------------------------------------------------------------------------------
+struct StageOps {
+    const double2 *blocks;   // [nblk][C][C] (fused: shared memory) or [H][C][C] (dense: global memory)
+    int nblk;
+    int stage_stride;        // in complex elements; 0 for the fused model
+};
+
+// Data of one QP instance that is not in the slab (targets and costs, pre-realified by a prep kernel).
+struct QPData {
+    const double *Q;      // stage cost Qbar(t) = Q + t*q_stride, t < H   [N][N] symmetric, realified
+    int q_stride;
+    const double *Qf;     // terminal cost
+    const double *R;      // R(t) = R + t*r_stride  [M][M] symmetric
+    int r_stride;
+    const double *r;      // realified targets r(t) = r + t*N, t <= H
+    const double *qlin;   // Qbar(t) r(t) for t < H:  qlin + t*N
+    const double *qlinf;  // Qf r(H)
+    const double *ub;     // control targets ub(t) = ub + t*M
+    const double *Rub;    // R(t) ub(t)
+    double sat;
+    int q_diag;           // 1 if every Qbar is diagonal (fast path of the line search / adjoint)
+};
+
+struct QPSet {
+    double rho, alpha, eps;
+    int max_admm, polish, max_polish;
+};
+
+struct Counters {
+    int admm, factor, polish, solves;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// out[i][j] = sum_k X[k][i] * Y[k][j], register tile TR x TC per lane, tiles round-robin over lanes.
+template <int TR, int TC, int NK, int NI, int NJ, class Sink>
+__device__ __forceinline__ void xty(const double *__restrict__ X, int ldx, const double *__restrict__ Y, int ldy,
+                                    int lane, Sink sink) {
+    constexpr int nti = cdiv(NI, TR), ntj = cdiv(NJ, TC);
+    for (int tile = lane; tile < nti * ntj; tile += 32) {
+        const int i0 = (tile / ntj) * TR, j0 = (tile % ntj) * TC;
+        double acc[TR][TC];
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+            for (int b = 0; b < TC; ++b) acc[a][b] = 0.0;
+        const double *xp = X + i0, *yp = Y + j0;
+#pragma unroll 2
+        for (int k = 0; k < NK; ++k) {
+            double xv[TR], yv[TC];
+#pragma unroll
+            for (int a = 0; a < TR; ++a) xv[a] = xp[k * ldx + a];
+#pragma unroll
+            for (int b = 0; b < TC; ++b) yv[b] = yp[k * ldy + b];
+#pragma unroll
+            for (int a = 0; a < TR; ++a)
+#pragma unroll
+                for (int b = 0; b < TC; ++b) acc[a][b] = fma(xv[a], yv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < TR; ++a)
+#pragma unroll
+            for (int b = 0; b < TC; ++b)
+                if (i0 + a < NI && j0 + b < NJ) sink(i0 + a, j0 + b, acc[a][b]);
+    }
+}
+
+// inverse of a small symmetric positive definite matrix held in registers (Gauss-Jordan, no pivoting)
+template <int M> __device__ __forceinline__ void spd_inverse(double (&a)[M][M], double (&inv)[M][M]) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j) inv[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int col = 0; col < M; ++col) {
+        const double piv = 1.0 / a[col][col];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            a[col][j] *= piv;
+            inv[col][j] *= piv;
+        }
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            if (r == col) continue;
+            const double f = a[r][col];
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                a[r][j] = fma(-f, a[col][j], a[r][j]);
+                inv[r][j] = fma(-f, inv[col][j], inv[r][j]);
+            }
+        }
+    }
+}
+
+// y[k] = (A_t x)[k] for lane k < N, x realified in shared memory.  Branch-free over the re/im halves.
+template <class CF>
+__device__ __forceinline__ double apply_A(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
+    constexpr int C = CF::C, N = CF::N;
+    if (lane >= N) return 0.0;
+    const int r = lane % C;
+    const bool im = lane >= C;
+    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + r * C;
+    double out = 0.0;
+    for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const double2 mij = blk[j];
+            const double a = im ? mij.y : mij.x;
+            const double b = im ? mij.x : -mij.y;
+            s0 = fma(a, x[j], s0);
+            s1 = fma(b, x[C + j], s1);
+        }
+        out = fma(phi_t[kb], s0 + s1, out);
+    }
+    return out;
+}
+
+// y[k] = (A_t^T v)[k] for lane k < N
+template <class CF>
+__device__ __forceinline__ double apply_AT(const StageOps &ops, const double *phi_t, int t, const double *v, int lane) {
+    constexpr int C = CF::C, N = CF::N;
+    if (lane >= N) return 0.0;
+    const int r = lane % C;
+    const bool im = lane >= C;
+    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + r;
+    double out = 0.0;
+    for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const double2 mjr = blk[j * C];
+            const double a = im ? -mjr.y : mjr.x;
+            const double b = im ? mjr.x : mjr.y;
+            s0 = fma(a, v[j], s0);
+            s1 = fma(b, v[C + j], s1);
+        }
+        out = fma(phi_t[kb], s0 + s1, out);
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bounds of the control box (optimize.py:29-30, :43)
+// ---------------------------------------------------------------------------------------------------------
+template <class CF> __device__ __forceinline__ double box_lo(const Slab<CF> &s, double sat, int t, int i) {
+    return t == 0 ? s.lo0[i] : -sat;
+}
+template <class CF> __device__ __forceinline__ double box_hi(const Slab<CF> &s, double sat, int t, int i) {
+    return t == 0 ? s.hi0[i] : sat;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Riccati matrix sweep.  masked: controls with mask != 0 are pinned to their bound (polish), rho_half = 0.
+// Produces K_t, S_t^-1, dv_t = P_{t+1} (D_t + B_fixed b) for all stages.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, double rho_half,
+                               bool masked, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q, LD = CF::LD;
+    for (int e = lane; e < N * N; e += 32) s.P[e] = qp.Qf[e];
+    for (int e = lane; e < N * (LD - Q); e += 32) {   // zero the padding columns once
+        const int k = e / (LD - Q), j = Q + e % (LD - Q);
+        s.AB[k * LD + j] = 0.0;
+    }
+    __syncwarp();
+    for (int t = H - 1; t >= 0; --t) {
+        const double *phi_t = s.phi + t * ops.nblk;
+        const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
+        // realified A_t into AB[:, 0:N]
+        for (int e = lane; e < C * C; e += 32) {
+            const int r = e / C, j = e % C;
+            double ar = 0.0, ai = 0.0;
+            for (int kb = 0; kb < ops.nblk; ++kb) {
+                const double2 v = blk0[kb * C * C + e];
+                ar = fma(phi_t[kb], v.x, ar);
+                ai = fma(phi_t[kb], v.y, ai);
+            }
+            s.AB[r * LD + j] = ar;
+            s.AB[r * LD + C + j] = -ai;
+            s.AB[(C + r) * LD + j] = ai;
+            s.AB[(C + r) * LD + C + j] = ar;
+        }
+        // B~ into AB[:, N:Q] and D~ into va
+        const double *Bt = s.B + t * N * M;
+        for (int e = lane; e < N * M; e += 32) {
+            const int k = e / M, i = e % M;
+            const bool fixed = masked && s.mask[t * M + i] != 0;
+            s.AB[k * LD + N + i] = fixed ? 0.0 : Bt[e];
+        }
+        if (lane < N) {
+            double dt = s.D[t * N + lane];
+            if (masked) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    const int mk = s.mask[t * M + i];
+                    if (mk) dt = fma(Bt[lane * M + i], mk == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
+                }
+            }
+            s.va[lane] = dt;
+        }
+        __syncwarp();
+        if (lane < N) {   // dv_t = P_{t+1} D~   (P symmetric: column access is conflict free)
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                a0 = fma(s.P[j * N + lane], s.va[j], a0);
+                a1 = fma(s.P[(j + 1) * N + lane], s.va[j + 1], a1);
+            }
+            s.dv[t * N + lane] = a0 + a1;
+        }
+        // W = P [A | B~]
+        xty<CF::TR1, CF::TC1, N, N, Q>(s.P, N, s.AB, LD, lane, [&](int i, int j, double v) { s.W[i * LD + j] = v; });
+        __syncwarp();
+        // [A | B~]^T W : T11 -> P, T21 -> T21, T22 -> S
+        xty<CF::TR2, CF::TC2, N, Q, Q>(s.AB, LD, s.W, LD, lane, [&](int i, int j, double v) {
+            if (j < N) {
+                if (i < N) s.P[i * N + j] = v;
+                else s.T21[(i - N) * N + j] = v;
+            } else if (i >= N) {
+                s.S[(i - N) * M + (j - N)] = v;
+            }
+        });
+        __syncwarp();
+        // S = R~ + rho/2 + B~^T P B~ ; invert (every lane redundantly, M <= 3)
+        double Sm[M][M], Si[M][M];
+        const double *Rt = qp.R + t * qp.r_stride;
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            const bool fa = masked && s.mask[t * M + a] != 0;
+#pragma unroll
+            for (int b = 0; b < M; ++b) {
+                const bool fb = masked && s.mask[t * M + b] != 0;
+                double v = 0.5 * (s.S[a * M + b] + s.S[b * M + a]);
+                if (fa || fb) v = (a == b) ? 1.0 : 0.0;
+                else v += Rt[a * M + b] + (a == b ? rho_half : 0.0);
+                Sm[a][b] = v;
+            }
+        }
+        spd_inverse<M>(Sm, Si);
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < M; ++a)
+#pragma unroll
+                for (int b = 0; b < M; ++b) s.Sinv[(t * M + a) * M + b] = Si[a][b];
+        }
+        if (lane < N) {
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+                double kv = 0.0;
+#pragma unroll
+                for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + lane], kv);
+                s.K[(t * M + a) * N + lane] = kv;
+            }
+        }
+        __syncwarp();
+        // P_t = Qbar_t + sym(T11) - T21^T K   (one lane per unordered pair keeps P exactly symmetric)
+        const double *Qt = qp.Q + t * qp.q_stride;
+        const double *Kt = s.K + t * M * N;
+        for (int e = lane; e < N * (N + 1) / 2; e += 32) {
+            // unrank e -> (i <= j)
+            int i = 0, rem = e;
+            while (rem >= N - i) { rem -= N - i; ++i; }
+            const int j = i + rem;
+            double v = 0.5 * (s.P[i * N + j] + s.P[j * N + i]) + Qt[i * N + j];
+#pragma unroll
+            for (int a = 0; a < M; ++a) v = fma(-s.T21[a * N + i], Kt[a * N + j], v);
+            s.P[i * N + j] = v;
+            s.P[j * N + i] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Vector sweeps: backward (costate) then forward (rollout).  POLISH selects the linear control term.
+// Writes Uo always, Xo if WRITE_X.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF, bool POLISH, bool WRITE_X>
+__device__ void riccati_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, double rho_half, int lane) {
+    constexpr int N = CF::N, M = CF::M;
+    double p = (lane < N) ? -qp.qlinf[lane] : 0.0;
+    for (int t = H - 1; t >= 0; --t) {
+        const double *phi_t = s.phi + t * ops.nblk;
+        const double *Bt = s.B + t * N * M;
+        const double v = (lane < N) ? s.dv[t * N + lane] + p : 0.0;
+        if (lane < N) s.va[lane] = v;
+        __syncwarp();
+        double g[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) g[i] = warp_sum(lane < N ? Bt[lane * M + i] * v : 0.0);
+        const double *Rt = qp.R + t * qp.r_stride;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            double h;
+            if (POLISH) {
+                // h_F = R_FF ub_F - R_F,fix (b - ub_fix); pinned controls come out as 0 and are overwritten by b
+                if (s.mask[t * M + i]) {
+                    g[i] = 0.0;
+                    continue;
+                }
+                h = 0.0;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const int mk = s.mask[t * M + j];
+                    const double ubj = qp.ub[t * M + j];
+                    h += mk ? -Rt[i * M + j] * ((mk == 1 ? box_lo(s, qp.sat, t, j) : box_hi(s, qp.sat, t, j)) - ubj)
+                            : Rt[i * M + j] * ubj;
+                }
+            } else {
+                h = qp.Rub[t * M + i] + rho_half * (s.z[t * M + i] - s.y[t * M + i]);
+            }
+            g[i] -= h;
+        }
+        const double atv = apply_AT<CF>(ops, phi_t, t, s.va, lane);
+        double kkv[M];
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            kkv[a] = 0.0;
+#pragma unroll
+            for (int b = 0; b < M; ++b) kkv[a] = fma(s.Sinv[(t * M + a) * M + b], g[b], kkv[a]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < M; ++a) s.kk[t * M + a] = kkv[a];
+        }
+        if (lane < N) {
+            double pn = atv - qp.qlin[t * N + lane];
+#pragma unroll
+            for (int a = 0; a < M; ++a) pn = fma(-s.K[(t * M + a) * N + lane], g[a], pn);
+            p = pn;
+        }
+        __syncwarp();
+    }
+    // forward
+    double x = (lane < N) ? s.x0[lane] : 0.0;
+    if (WRITE_X && lane < N) s.Xo[lane] = x;
+    for (int t = 0; t < H; ++t) {
+        const double *phi_t = s.phi + t * ops.nblk;
+        const double *Bt = s.B + t * N * M;
+        if (lane < N) s.va[lane] = x;
+        __syncwarp();
+        double u[M];
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            u[a] = -warp_sum(lane < N ? s.K[(t * M + a) * N + lane] * x : 0.0) - s.kk[t * M + a];
+            if (POLISH) {
+                const int mk = s.mask[t * M + a];
+                if (mk) u[a] = mk == 1 ? box_lo(s, qp.sat, t, a) : box_hi(s, qp.sat, t, a);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < M; ++a) s.Uo[t * M + a] = u[a];
+        }
+        const double ax = apply_A<CF>(ops, phi_t, t, s.va, lane);
+        if (lane < N) {
+            double xn = ax + s.D[t * N + lane];
+#pragma unroll
+            for (int a = 0; a < M; ++a) xn = fma(Bt[lane * M + a], u[a], xn);
+            x = xn;
+            if (WRITE_X) s.Xo[(t + 1) * N + lane] = x;
+        }
+        __syncwarp();
+    }
+}
+
+// (Qbar v)[lane] for v in shared memory
+template <class CF>
+__device__ __forceinline__ double apply_Q(const double *Qm, int q_diag, const double *v, int lane) {
+    constexpr int N = CF::N;
+    if (lane >= N) return 0.0;
+    if (q_diag) return Qm[lane * N + lane] * v[lane];
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        a0 = fma(Qm[j * N + lane], v[j], a0);
+        a1 = fma(Qm[(j + 1) * N + lane], v[j + 1], a1);
+    }
+    return a0 + a1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adjoint gradient of the condensed cost at (Xo, Uo) -> s.kk[t*M+i] (re-used as scratch); returns max |grad|.
+//   lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};  lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ double adjoint_gradient(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, int lane) {
+    constexpr int N = CF::N, M = CF::M;
+    if (lane < N) s.vb[lane] = s.Xo[H * N + lane] - qp.r[H * N + lane];
+    __syncwarp();
+    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.vb, lane);
+    double gmax = 0.0;
+    for (int t = H - 1; t >= 0; --t) {
+        const double *phi_t = s.phi + t * ops.nblk;
+        const double *Bt = s.B + t * N * M;
+        const double *Rt = qp.R + t * qp.r_stride;
+        __syncwarp();
+        if (lane < N) {
+            s.va[lane] = lam;
+            s.vb[lane] = s.Xo[t * N + lane] - qp.r[t * N + lane];
+        }
+        __syncwarp();
+        double g[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) g[i] = warp_sum(lane < N ? Bt[lane * M + i] * lam : 0.0);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) g[i] = fma(2.0 * Rt[i * M + j], s.Uo[t * M + j] - qp.ub[t * M + j], g[i]);
+            gmax = fmax(gmax, fabs(g[i]));
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) s.kk[t * M + i] = g[i];
+        }
+        const double atl = apply_AT<CF>(ops, phi_t, t, s.va, lane);
+        lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, s.vb, lane);
+    }
+    __syncwarp();
+    return gmax;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The QP: ADMM blocks (warp-vote convergence) + active-set polish with KKT certificate.
+// In: slab {B, D, phi, x0, lo0, hi0, z, y(warm)}.  Out: Xo, Uo; z, y updated.  Returns status 0 / 2 / 3.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp, const QPSet &set, int H, int lane,
+                        Counters &cnt) {
+    constexpr int N = CF::N, M = CF::M;
+    const int HM = H * M;
+    const double rho_half = 0.5 * set.rho;
+    // clip the warm start into the current box
+    for (int e = lane; e < HM; e += 32) {
+        const int t = e / M, i = e % M;
+        s.z[e] = fmin(fmax(s.z[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+    }
+    __syncwarp();
+    riccati_factor<CF>(s, ops, qp, H, rho_half, false, lane);
+    cnt.factor++;
+    cnt.solves++;
+    double eps = set.eps;
+    int status = 0;
+    bool admm_factor_valid = true;
+    for (;;) {
+        if (!admm_factor_valid) {
+            riccati_factor<CF>(s, ops, qp, H, rho_half, false, lane);
+            cnt.factor++;
+            admm_factor_valid = true;
+        }
+        for (int it = 0; it < set.max_admm; ++it) {
+            if (set.polish) riccati_solve<CF, false, false>(s, ops, qp, H, rho_half, lane);
+            else riccati_solve<CF, false, true>(s, ops, qp, H, rho_half, lane);
+            cnt.admm++;
+            bool bad = false;
+            for (int e = lane; e < HM; e += 32) {
+                const int t = e / M, i = e % M;
+                const double u = s.Uo[e], zo = s.z[e];
+                const double uh = set.alpha * u + (1.0 - set.alpha) * zo;
+                const double zn = fmin(fmax(uh + s.y[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+                s.y[e] += uh - zn;
+                s.z[e] = zn;
+                bad |= !(fabs(u - zn) < eps) || !(set.rho * fabs(zn - zo) < eps);
+            }
+            __syncwarp();
+            if (!__any_sync(FULL, bad)) break;   // warp vote: every lane's slice of the residuals is below eps
+        }
+        if (!set.polish) {
+            // OSQP-equivalent mode: report the feasible iterate z and its rollout
+            for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
+            __syncwarp();
+            // rollout with u = z: reuse the forward pass by a plain model rollout
+            double x = (lane < N) ? s.x0[lane] : 0.0;
+            if (lane < N) s.Xo[lane] = x;
+            for (int t = 0; t < H; ++t) {
+                if (lane < N) s.va[lane] = x;
+                __syncwarp();
+                const double ax = apply_A<CF>(ops, s.phi + t * ops.nblk, t, s.va, lane);
+                if (lane < N) {
+                    double xn = ax + s.D[t * N + lane];
+#pragma unroll
+                    for (int a = 0; a < M; ++a) xn = fma(s.B[(t * N + lane) * M + a], s.Uo[t * M + a], xn);
+                    x = xn;
+                    s.Xo[(t + 1) * N + lane] = x;
+                }
+                __syncwarp();
+            }
+            break;
+        }
+        // ---- polish: primal-dual active set seeded by the ADMM estimate
+        for (int e = lane; e < HM; e += 32) {
+            const int t = e / M, i = e % M;
+            const double zz = s.z[e], yy = s.y[e];
+            int mk = 0;
+            if (zz <= box_lo(s, qp.sat, t, i) && yy < 0.0) mk = 1;
+            else if (zz >= box_hi(s, qp.sat, t, i) && yy > 0.0) mk = 2;
+            s.mask[e] = mk;
+        }
+        __syncwarp();
+        bool certified = false;
+        for (int round = 0; round < set.max_polish; ++round) {
+            riccati_factor<CF>(s, ops, qp, H, 0.0, true, lane);
+            admm_factor_valid = false;
+            cnt.factor++;
+            cnt.polish++;
+            riccati_solve<CF, true, true>(s, ops, qp, H, 0.0, lane);
+            const double gmax = adjoint_gradient<CF>(s, ops, qp, H, lane);
+            const double gs = fmax(1.0, gmax);
+            bool changed = false;
+            for (int e = lane; e < HM; e += 32) {
+                const int t = e / M, i = e % M;
+                const int mk = s.mask[e];
+                const double u = s.Uo[e], g = s.kk[e];
+                const double lo = box_lo(s, qp.sat, t, i), hi = box_hi(s, qp.sat, t, i);
+                int nm = mk;
+                if (mk == 0) {
+                    if (u < lo - 1e-12) nm = 1;
+                    else if (u > hi + 1e-12) nm = 2;
+                } else if (mk == 1) {
+                    if (g < -1e-10 * gs) nm = 0;
+                } else {
+                    if (g > 1e-10 * gs) nm = 0;
+                }
+                if (nm != mk) {
+                    s.mask[e] = nm;
+                    changed = true;
+                }
+            }
+            __syncwarp();
+            if (!__any_sync(FULL, changed)) {
+                certified = true;
+                break;
+            }
+        }
+        if (certified) {
+            for (int e = lane; e < HM; e += 32) {
+                const int t = e / M, i = e % M;
+                s.z[e] = fmin(fmax(s.Uo[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+            }
+            __syncwarp();
+            break;
+        }
+        eps *= 0.1;
+        if (eps < 1e-10) {
+            status = 2;   // could not certify: report the ADMM iterate (reference: solver warning -> exit code 2)
+            for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
+            __syncwarp();
+            break;
+        }
+    }
+    // non-finite result -> reference exit code 3 (mpc.py:200-203)
+    bool nonfinite = false;
+    for (int e = lane; e < HM; e += 32) nonfinite |= !isfinite(s.Uo[e]);
+    for (int e = lane; e < (H + 1) * N; e += 32) nonfinite |= !isfinite(s.Xo[e]);
+    if (__any_sync(FULL, nonfinite)) status = 3;
+    return status;
+}
+
+// objective value sum (x-r)^T Q (x-r) + (u-ub)^T R (u-ub)  (optimize.py:34-35, :54; no 1/2)
+template <class CF>
+__device__ double qp_objective(const Slab<CF> &s, const QPData &qp, int H, int lane) {
+    constexpr int N = CF::N, M = CF::M;
+    double acc = 0.0;
+    for (int t = 0; t <= H; ++t) {
+        __syncwarp();
+        if (lane < N) s.vb[lane] = s.Xo[t * N + lane] - qp.r[t * N + lane];
+        __syncwarp();
+        const double qv = apply_Q<CF>(t == H ? qp.Qf : qp.Q + t * qp.q_stride, qp.q_diag, s.vb, lane);
+        if (lane < N) acc = fma(qv, s.vb[lane], acc);
+    }
+    for (int e = lane; e < H * M; e += 32) {
+        const int t = e / M, i = e % M;
+        const double *Rt = qp.R + t * qp.r_stride;
+        double rv = 0.0;
+        for (int j = 0; j < M; ++j) rv = fma(Rt[i * M + j], s.Uo[t * M + j] - qp.ub[t * M + j], rv);
+        acc = fma(rv, s.Uo[e] - qp.ub[e], acc);
+    }
+    return warp_sum(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Linearisation of the bilinear model along (Xg, Ug): fills phi, B, D  (linearize.py:50-70).
+//   B_t[:, i] = sum_k pow[k][i] * prod_l u_l^(pow[k][l] - [l == i]) * (N_k x_t);  D_t = -B_t u_t.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ void linearize(const Slab<CF> &s, const StageOps &model, const int *pow, int H, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    const int p = model.nblk - 1;
+    for (int t = 0; t < H; ++t) {
+        // monomials and derivative weights: lane k < p computes its own
+        double *dco = s.scr;   // [p][M]
+        if (lane < p) {
+            double phi = 1.0;
+            double dw[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) dw[i] = (double)pow[lane * M + i];
+#pragma unroll
+            for (int l = 0; l < M; ++l) {
+                const int e = pow[lane * M + l];
+                const double ul = s.Ug[t * M + l];
+                double pw = 1.0, pwm1 = 1.0;   // u^e and u^(e-1)
+                for (int q = 0; q < e; ++q) {
+                    pwm1 = pw;
+                    pw *= ul;
+                }
+                phi *= pw;
+#pragma unroll
+                for (int i = 0; i < M; ++i) dw[i] *= (i == l) ? (e > 0 ? pwm1 : 0.0) : pw;
+            }
+            s.phi[t * model.nblk + 1 + lane] = phi;
+#pragma unroll
+            for (int i = 0; i < M; ++i) dco[lane * M + i] = dw[i];
+        }
+        if (lane == 0) s.phi[t * model.nblk] = 1.0;
+        __syncwarp();
+        if (lane < N) {
+            const int r = lane % C;
+            const bool im = lane >= C;
+            const double *x = s.Xg + t * N;
+            double b[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) b[i] = 0.0;
+            for (int kb = 1; kb <= p; ++kb) {
+                const double2 *blk = model.blocks + (kb * C + r) * C;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const double2 mij = blk[j];
+                    s0 = fma(im ? mij.y : mij.x, x[j], s0);
+                    s1 = fma(im ? mij.x : -mij.y, x[C + j], s1);
+                }
+                const double y = s0 + s1;
+#pragma unroll
+                for (int i = 0; i < M; ++i) b[i] = fma(dco[(kb - 1) * M + i], y, b[i]);
+            }
+            double d = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                s.B[(t * N + lane) * M + i] = b[i];
+                d = fma(-b[i], s.Ug[t * M + i], d);
+            }
+            s.D[t * N + lane] = d;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Line search (mpc.py:101-125): alpha = -(M (Zg - Zt)) . DZ / (DZ . M DZ), step = |alpha| ||DZ||_2 with
+// M = blockdiag(Qbar_0..Qbar_H, [[R,0],[0,R]]_0..) in TIME-major order while Z is the STATE-major flattening
+// [Re X.ravel(), Im X.ravel(), Re U.ravel(), Im U.ravel()] of X [c][H+1], U [m][H].  Reproduced as is.
+// X arrays here are [t][N] realified; r = qp.r.  Z index zeta -> (t, k): part = zeta / (C*(H+1)),
+// rem = zeta % (C*(H+1)), state = rem / (H+1), t = rem % (H+1), k = part*C + state.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ void line_search(const Slab<CF> &s, const QPData &qp, int H, int lane, double &alpha, double &step) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    double num = 0.0, den = 0.0, nrm = 0.0;
+    const int H1 = H + 1;
+    for (int tau = 0; tau <= H; ++tau) {
+        double e_k = 0.0, d_k = 0.0;
+        if (lane < N) {
+            const int zeta = tau * N + lane;
+            const int part = zeta / (C * H1), rem = zeta % (C * H1);
+            const int st = rem / H1, t = rem % H1;
+            const int idx = t * N + part * C + st;
+            const double xg = s.Xg[idx];
+            e_k = xg - qp.r[idx];
+            d_k = s.Xo[idx] - xg;
+            nrm = fma(d_k, d_k, nrm);
+        }
+        const double *Qt = (tau == H) ? qp.Qf : qp.Q + tau * qp.q_stride;
+        if (qp.q_diag) {
+            if (lane < N) {
+                const double qd = Qt[lane * N + lane];
+                num = fma(qd * e_k, d_k, num);
+                den = fma(qd * d_k, d_k, den);
+            }
+        } else {
+            __syncwarp();
+            if (lane < N) {
+                s.va[lane] = e_k;
+                s.vb[lane] = d_k;
+            }
+            __syncwarp();
+            if (lane < N) {
+                double qe = 0.0, qd = 0.0;
+                for (int j = 0; j < N; ++j) {
+                    const double qv = Qt[lane * N + j];
+                    qe = fma(qv, s.va[j], qe);
+                    qd = fma(qv, s.vb[j], qd);
+                }
+                num = fma(qe, d_k, num);
+                den = fma(qd, d_k, den);
+            }
+        }
+    }
+    // control part: Z_U = [U.ravel() (index i*H + t), zeros(mH)], blocks tau < H of size 2M: [[R,0],[0,R]]
+    const int HM = H * M;
+    for (int tau = 0; tau < H; ++tau) {
+        const double *Rt = qp.R + tau * qp.r_stride;
+        if (lane < 2 * M) {
+            const int a = lane;
+            const int blk_row = a / M, ia = a % M;   // block row 0: real rows, 1: imaginary rows
+            const int za = tau * 2 * M + a;
+            double da = 0.0;
+            if (za < HM) {
+                const int i = za / H, t = za % H;
+                da = s.Uo[t * M + i] - s.Ug[t * M + i];
+            }
+            double re = 0.0, rd = 0.0;
+            for (int jb = 0; jb < M; ++jb) {
+                const int zb = tau * 2 * M + blk_row * M + jb;
+                if (zb < HM) {
+                    const int i = zb / H, t = zb % H;
+                    const double ug = s.Ug[t * M + i];
+                    re = fma(Rt[ia * M + jb], ug - qp.ub[t * M + i], re);
+                    rd = fma(Rt[ia * M + jb], s.Uo[t * M + i] - ug, rd);
+                }
+            }
+            num = fma(re, da, num);
+            den = fma(rd, da, den);
+        }
+    }
+    for (int e = lane; e < HM; e += 32) {
+        const double d = s.Uo[e] - s.Ug[e];
+        nrm = fma(d, d, nrm);
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    nrm = warp_sum(nrm);
+    if (den == 0.0) {   // reference would produce 0/0; treat a vanishing direction as converged
+        alpha = 0.0;
+        step = 0.0;
+    } else {
+        alpha = -num / den;
+        step = fabs(alpha) * sqrt(nrm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Small complex matrices for the plant: d <= 4, entries distributed one per lane (lane = i*d + j).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+// out(i,j) = sum_k A[i][k] B[k][j] (lane holds out entry); A, B in shared memory as double2 [d*d]
+__device__ __forceinline__ double2 cmm(const double2 *A, const double2 *B, int d, int i, int j) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int k = 0; k < d; ++k) acc = cfma(A[i * d + k], B[k * d + j], acc);
+    return acc;
+}
+
+// U = expm(-i H dt) for Hermitian-or-not H (d x d) by scaling and squaring of a degree-16 Taylor polynomial.
+// Hm, T0, T1: shared scratch [d*d] double2 each.  Result left in T0.  All 32 lanes must call.
+__device__ void expm_minus_i(const double2 *Hm, double dt, int d, double2 *G, double2 *T0, double2 *T1, int lane) {
+    const int dd = d * d;
+    const int i = lane / d, j = lane % d;
+    const bool act = lane < dd;
+    // G = -i H dt ; 1-norm
+    double2 g = make_double2(0.0, 0.0);
+    if (act) {
+        const double2 h = Hm[lane];
+        g = make_double2(h.y * dt, -h.x * dt);
+    }
+    double colsum = act ? hypot(g.x, g.y) : 0.0;
+    // column sums: reduce over i for fixed j
+    if (act) T1[lane] = make_double2(colsum, 0.0);
+    __syncwarp();
+    double nrm = 0.0;
+    if (act) {
+        double cs = 0.0;
+        for (int k = 0; k < d; ++k) cs += T1[k * d + j].x;
+        nrm = cs;
+    }
+    nrm = warp_max(nrm);
+    int sq = 0;
+    while (nrm > 0.5 && sq < 40) {
+        nrm *= 0.5;
+        ++sq;
+    }
+    const double sc = ldexp(1.0, -sq);
+    g.x *= sc;
+    g.y *= sc;
+    __syncwarp();
+    if (act) {
+        G[lane] = g;
+        T0[lane] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    }
+    __syncwarp();
+    // Horner: T = I + G/1 (I + G/2 (I + ... (I + G/16)))   (||G|| <= 0.5: remainder 0.5^17/17! ~ 2e-20)
+    for (int k = 16; k >= 1; --k) {
+        double2 v = make_double2(0.0, 0.0);
+        if (act) {
+            v = cmm(G, T0, d, i, j);
+            const double inv = 1.0 / (double)k;
+            v.x = fma(v.x, inv, i == j ? 1.0 : 0.0);
+            v.y *= inv;
+        }
+        __syncwarp();
+        if (act) T0[lane] = v;
+        __syncwarp();
+    }
+    for (int q = 0; q < sq; ++q) {
+        double2 v = make_double2(0.0, 0.0);
+        if (act) v = cmm(T0, T0, d, i, j);
+        __syncwarp();
+        if (act) T0[lane] = v;
+        __syncwarp();
+    }
+}
+
+// rho <- U rho U^dagger ; rho in shared (double2 [dd]), U in shared; tmp scratch
+__device__ void conjugate(double2 *rho, const double2 *U, int d, double2 *tmp, int lane) {
+    const int dd = d * d;
+    const int i = lane / d, j = lane % d;
+    const bool act = lane < dd;
+    if (act) tmp[lane] = cmm(U, rho, d, i, j);
+    __syncwarp();
+    double2 v = make_double2(0.0, 0.0);
+    if (act) {
+        for (int k = 0; k < d; ++k) {
+            const double2 uc = U[j * d + k];
+            v = cfma(tmp[i * d + k], make_double2(uc.x, -uc.y), v);
+        }
+    }
+    __syncwarp();
+    if (act) rho[lane] = v;
+    __syncwarp();
+}
+
+}  // namespace m4q

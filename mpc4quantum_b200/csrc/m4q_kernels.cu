@@ -1,0 +1,1256 @@
+// libm4q: kernels and C ABI of the B200-native MPC4quantum hot path (sm_100a).
+//
+// One warp owns one ensemble member (or one QP instance); everything a member needs between the first
+// linearisation and the last plant step lives in a warp-private slab of shared memory, so the closed loop of
+// mpc4quantum/mpc.py:128-304 runs without leaving the SM.  The device building blocks are in m4q_core.cuh; this
+// file holds the kernels, the launch geometry and the extern "C" entry points declared in include/m4q.h.
+#include "m4q_core.cuh"
+#include "../../include/m4q.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace m4q {
+
+static thread_local std::string g_err;
+
+static int fail(const std::string &msg) {
+    g_err = msg;
+    return -1;
+}
+#define M4Q_CUDA(call)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared tables of one closed-loop problem (member independent), built once per launch by build_tables.
+// Layout in doubles; offsets from TableLayout.
+// ---------------------------------------------------------------------------------------------------------
+struct TableLayout {
+    int Qr, Qfr, Rr, r, qlin, qlinf, ub, Rub, flags, total;
+    __host__ __device__ TableLayout(int N, int M, int n_targ) {
+        int o = 0;
+        auto take = [&](int cnt) {
+            int at = o;
+            o += rup(cnt, 2);
+            return at;
+        };
+        Qr = take(N * N);
+        Qfr = take(N * N);
+        Rr = take(M * M);
+        r = take(n_targ * N);
+        qlin = take(n_targ * N);
+        qlinf = take(n_targ * N);
+        ub = take(n_targ * M);
+        Rub = take(n_targ * M);
+        flags = take(4);   // [0] q_diag, [1..2] work counter (as int)
+        total = o;
+    }
+};
+
+// realified, symmetrised cost block: M = [[Re, -Im], [Im, Re]], out = (M + M^T) / 2
+__device__ __forceinline__ double realified_sym(const double2 *Qc, int C, int i, int j) {
+    auto entry = [&](int a, int b) {
+        const int ra = a % C, rb = b % C;
+        const double2 v = Qc[ra * C + rb];
+        if (a < C) return b < C ? v.x : -v.y;
+        return b < C ? v.y : v.x;
+    };
+    return 0.5 * (entry(i, j) + entry(j, i));
+}
+
+__global__ void build_tables(int C, int M, int n_targ, const double2 *Q, const double2 *Qf, const double *R,
+                             const double2 *X_targ, const double *U_targ, double *tab) {
+    const int N = 2 * C;
+    const TableLayout L(N, M, n_targ);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < N * N; e += nt) {
+        tab[L.Qr + e] = realified_sym(Q, C, e / N, e % N);
+        tab[L.Qfr + e] = realified_sym(Qf, C, e / N, e % N);
+    }
+    for (int e = tid; e < M * M; e += nt) tab[L.Rr + e] = 0.5 * (R[e] + R[(e % M) * M + e / M]);
+    for (int e = tid; e < n_targ * N; e += nt) {
+        const int col = e / N, k = e % N;
+        const double2 v = X_targ[(k % C) * n_targ + col];
+        tab[L.r + e] = k < C ? v.x : v.y;
+    }
+    for (int e = tid; e < n_targ * M; e += nt) {
+        const int col = e / M, i = e % M;
+        tab[L.ub + e] = col < n_targ - 1 ? U_targ[i * (n_targ - 1) + col] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < n_targ * N; e += nt) {
+        const int col = e / N, k = e % N;
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < N; ++j) {
+            const double rv = tab[L.r + col * N + j];
+            a = fma(tab[L.Qr + k * N + j], rv, a);
+            b = fma(tab[L.Qfr + k * N + j], rv, b);
+        }
+        tab[L.qlin + e] = a;
+        tab[L.qlinf + e] = b;
+    }
+    for (int e = tid; e < n_targ * M; e += nt) {
+        const int col = e / M, i = e % M;
+        double a = 0.0;
+        for (int j = 0; j < M; ++j) a = fma(tab[L.Rr + i * M + j], tab[L.ub + col * M + j], a);
+        tab[L.Rub + e] = a;
+    }
+    if (tid == 0) {
+        bool diag = true;
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j)
+                if (i != j && (tab[L.Qr + i * N + j] != 0.0 || tab[L.Qfr + i * N + j] != 0.0)) diag = false;
+        tab[L.flags] = diag ? 1.0 : 0.0;
+        int *ctr = reinterpret_cast<int *>(tab + L.flags + 1);
+        ctr[0] = 0;
+        ctr[1] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Observable maps (experiment.py:29-37, 225-235, 248-306).  plant state: double2 [d*d] in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+// model state (realified, length 2C) <- lift(plant state)
+template <class CF>
+__device__ void lift_state(int mode, int d, const double2 *rho, double *out, int lane) {
+    constexpr int C = CF::C;
+    if (mode == M4Q_LIFT_IDENTITY) {
+        if (lane < C) {
+            out[lane] = rho[lane].x;
+            out[C + lane] = rho[lane].y;
+        }
+    } else if (mode == M4Q_LIFT_COUPLED) {
+        // d = dA*dA; stacked [vec(tr_B rho), vec(tr_A rho)], C = 2*dA*dA
+        const int dA = (d == 4) ? 2 : (d == 9 ? 3 : 1);
+        const int half = dA * dA;
+        if (lane < 2 * half) {
+            const int which = lane / half, e = lane % half, a = e / dA, b = e % dA;
+            double2 acc = make_double2(0.0, 0.0);
+            for (int k = 0; k < dA; ++k) {
+                // which = 0: rhoA[a][b] = sum_k rho[(a,k),(b,k)];  which = 1: rhoB[a][b] = sum_k rho[(k,a),(k,b)]
+                const int row = which == 0 ? a * dA + k : k * dA + a;
+                const int col = which == 0 ? b * dA + k : k * dA + b;
+                const double2 v = rho[row * d + col];
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            out[lane] = acc.x;
+            out[C + lane] = acc.y;
+        }
+    } else {   // M4Q_LIFT_TRUNC32: qubit block of a qutrit divided by its trace norm (sum of singular values)
+        const double2 a = rho[0], b = rho[1], c = rho[3], e = rho[4];
+        const double fro = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + e.x * e.x + e.y * e.y;
+        const double2 ae = cmul(a, e), bc = cmul(b, c);
+        const double det = hypot(ae.x - bc.x, ae.y - bc.y);
+        const double nrm = sqrt(fro + 2.0 * det);
+        if (lane < 4) {
+            const double2 v = rho[(lane / 2) * 3 + lane % 2];
+            out[lane] = v.x / nrm;
+            out[C + lane] = v.y / nrm;
+        }
+    }
+    __syncwarp();
+}
+
+// plant state <- proj(model state)
+template <class CF>
+__device__ void proj_state(int mode, int d, const double *x, double2 *rho, int lane) {
+    constexpr int C = CF::C;
+    if (mode == M4Q_LIFT_COUPLED) {
+        const int dA = (d == 4) ? 2 : (d == 9 ? 3 : 1);
+        const int half = dA * dA;
+        if (lane < d * d) {
+            const int row = lane / d, col = lane % d;
+            const int a = row / dA, b = row % dA, a2 = col / dA, b2 = col % dA;
+            const double2 ra = make_double2(x[a * dA + a2], x[C + a * dA + a2]);
+            const double2 rb = make_double2(x[half + b * dA + b2], x[C + half + b * dA + b2]);
+            rho[lane] = cmul(ra, rb);
+        }
+    } else {
+        if (lane < C) rho[lane] = make_double2(x[lane], x[C + lane]);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The closed loop kernel
+// ---------------------------------------------------------------------------------------------------------
+struct MpcArgs {
+    int H, S, mf, warm_start, max_iter, lift_mode, has_du, n_targ, d, nblk;
+    double dt, sat, du, exit_infid;
+    QPSet set;
+    const double2 *A_blocks;
+    const int *powers;
+    const double2 *fid_vec;
+    double *tab;
+    long long n_members;
+    const double2 *x0;
+    int x0_shared;
+    const double2 *H0, *H1;
+    int shared_ham;
+    int step_begin, step_end, external_plant;
+    double2 *xs;
+    double *us;
+    int *exit_code, *steps_done, *qp_count, *counters;
+    double *fidelity;
+    double *state;
+    int slab_doubles, shared_doubles;
+};
+
+template <class CF>
+__global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    extern __shared__ double2 smem2[];
+    double *smem = reinterpret_cast<double *>(smem2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = a.H, S = a.S, d = a.d, dd = d * d;
+    const int xdim = a.external_plant ? C : dd;   // length of one xs column
+    const TableLayout L(N, M, a.n_targ);
+
+    // ---- CTA-shared, read-only: model blocks, monomial exponents, cost matrices
+    double2 *blocks = reinterpret_cast<double2 *>(smem);
+    double *Qr = smem + 2 * a.nblk * C * C;
+    double *Qfr = Qr + N * N;
+    double *Rr = Qfr + N * N;
+    int *pow = reinterpret_cast<int *>(Rr + rup(M * M, 2));
+    for (int e = threadIdx.x; e < a.nblk * C * C; e += blockDim.x) blocks[e] = a.A_blocks[e];
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        Qr[e] = a.tab[L.Qr + e];
+        Qfr[e] = a.tab[L.Qfr + e];
+    }
+    for (int e = threadIdx.x; e < M * M; e += blockDim.x) Rr[e] = a.tab[L.Rr + e];
+    for (int e = threadIdx.x; e < (a.nblk - 1) * M; e += blockDim.x) pow[e] = a.powers[e];
+    __syncthreads();
+
+    Slab<CF> s;
+    Slab<CF>::layout(&s, smem + a.shared_doubles + (size_t)warp * a.slab_doubles, H, a.nblk, cmax(dd, C));
+    double2 *xcur = reinterpret_cast<double2 *>(s.xcur);
+    double2 *xmeas = reinterpret_cast<double2 *>(s.xmeas);
+    double2 *scr2 = reinterpret_cast<double2 *>(s.scr);
+
+    StageOps model;
+    model.blocks = blocks;
+    model.nblk = a.nblk;
+    model.stage_stride = 0;
+
+    int *work = reinterpret_cast<int *>(a.tab + L.flags + 1);
+    const int q_diag = a.tab[L.flags] != 0.0;
+    const int persist = Slab<CF>::persistent_doubles(H, cmax(dd, C));
+
+    for (;;) {
+        long long k = 0;
+        if (lane == 0) k = atomicAdd(work, 1);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= a.n_members) break;
+
+        Counters cnt = {0, 0, 0, 0};
+        int exit_code = 0;
+        double2 *xs_k = a.xs + (size_t)k * xdim * (S + 1);
+        double *us_k = a.us + (size_t)k * M * S;
+        const double2 *H0k = a.H0 ? a.H0 + (a.shared_ham ? 0 : (size_t)k * dd) : nullptr;
+        const double2 *H1k = a.H1 ? a.H1 + (a.shared_ham ? 0 : (size_t)k * M * dd) : nullptr;
+
+        // ---- initial or restored loop state
+        if (a.step_begin == 0) {
+            const double2 *x0k = a.x0 + (a.x0_shared ? 0 : (size_t)k * xdim);
+            if (lane < xdim) {
+                const double2 v = x0k[lane];
+                xcur[lane] = v;
+                xmeas[lane] = v;
+                xs_k[(size_t)lane * (S + 1)] = v;
+            }
+            __syncwarp();
+            lift_state<CF>(a.external_plant ? M4Q_LIFT_IDENTITY : a.lift_mode, d, xcur, s.x0, lane);
+            for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = s.x0[e % N];   // mpc.py:141
+            for (int e = lane; e < H * M; e += 32) {                              // mpc.py:142
+                s.Ug[e] = 0.0;
+                s.z[e] = 0.0;
+                s.y[e] = 0.0;
+            }
+        } else {
+            const double *st = a.state + (size_t)k * persist;
+            int o = 0;
+            for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = st[o + e];
+            o += (H + 1) * N;
+            for (int e = lane; e < H * M; e += 32) {
+                s.Ug[e] = st[o + e];
+                s.z[e] = st[o + H * M + e];
+                s.y[e] = st[o + 2 * H * M + e];
+            }
+            o += 3 * H * M;
+            if (lane < xdim) {
+                // the caller may have written xs[:, step_begin] (external plant); the measured state is read from xs
+                xcur[lane] = xs_k[(size_t)lane * (S + 1) + a.step_begin];
+                xmeas[lane] = make_double2(st[o + 2 * lane], st[o + 2 * lane + 1]);
+            }
+            exit_code = a.exit_code[k];
+        }
+        __syncwarp();
+
+        int step = a.step_begin;
+        if (exit_code == 0) {
+            for (; step < a.step_end; ++step) {
+                // reference windows lag by one step (mpc.py:145-146, :276-277)
+                const int w0 = step == 0 ? 0 : step - 1;
+                QPData qp;
+                qp.Q = Qr;
+                qp.q_stride = 0;
+                qp.Qf = Qfr;
+                qp.R = Rr;
+                qp.r_stride = 0;
+                qp.r = a.tab + L.r + (size_t)w0 * N;
+                qp.qlin = a.tab + L.qlin + (size_t)w0 * N;
+                qp.qlinf = a.tab + L.qlinf + (size_t)(w0 + H) * N;
+                qp.ub = a.tab + L.ub + (size_t)w0 * M;
+                qp.Rub = a.tab + L.Rub + (size_t)w0 * M;
+                qp.sat = a.sat;
+                qp.q_diag = q_diag;
+
+                // measured state -> model space: the QP's initial condition (mpc.py:187)
+                lift_state<CF>(a.external_plant ? M4Q_LIFT_IDENTITY : a.lift_mode, d, xcur, s.x0, lane);
+                // rate bound centred on us[step-1], or on the reference control for step <= 1 (mpc.py:185)
+                if (lane < M) {
+                    double lo = -a.sat, hi = a.sat;
+                    if (a.has_du) {
+                        const double up = step > 1 ? us_k[lane * S + step - 1] : qp.ub[lane];
+                        lo = fmax(lo, up - a.du);
+                        hi = fmin(hi, up + a.du);
+                    }
+                    s.lo0[lane] = lo;
+                    s.hi0[lane] = hi;
+                }
+                __syncwarp();
+
+                int n_iter = 0;
+                bool done = false;
+                while (!done && n_iter < a.max_iter) {
+                    linearize<CF>(s, model, pow, H, lane);                      // mpc.py:175
+                    const int status = qp_solve<CF>(s, model, qp, a.set, H, lane, cnt);   // mpc.py:189
+                    if (status != 0) {
+                        exit_code = status;
+                        break;
+                    }
+                    double alpha = 1.0;
+                    if (step > 1 && a.warm_start) {                             // mpc.py:208-212
+                        done = true;
+                    } else {
+                        double stp;
+                        line_search<CF>(s, qp, H, lane, alpha, stp);            // mpc.py:215
+                        done = stp < 1e-4;                                      // mpc.py:224
+                    }
+                    for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = fma(alpha, s.Xo[e] - s.Xg[e], s.Xg[e]);
+                    for (int e = lane; e < H * M; e += 32) s.Ug[e] = fma(alpha, s.Uo[e] - s.Ug[e], s.Ug[e]);
+                    __syncwarp();
+                    ++n_iter;
+                }
+                if (exit_code != 0) break;
+                if (lane == 0) a.qp_count[(size_t)k * S + step] = n_iter;
+
+                // apply the first control of the last QP (mpc.py:250)
+                if (lane < M) us_k[lane * S + step] = s.Uo[lane];
+                __syncwarp();
+
+                if (!a.external_plant) {
+                    if ((step + 1) % a.mf == 0) {
+                        // plant window, newest control first (mpc.py:257): segment j uses us[step - j]
+                        for (int j = 0; j < a.mf; ++j) {
+                            if (lane < dd) {
+                                double2 h = H0k[lane];
+                                for (int i = 0; i < M; ++i) {
+                                    const double u = us_k[i * S + step - j];
+                                    const double2 h1 = H1k[i * dd + lane];
+                                    h.x = fma(u, h1.x, h.x);
+                                    h.y = fma(u, h1.y, h.y);
+                                }
+                                scr2[lane] = h;
+                            }
+                            __syncwarp();
+                            expm_minus_i(scr2, a.dt, d, scr2 + dd, scr2 + 2 * dd, scr2 + 3 * dd, lane);
+                            conjugate(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
+                        }
+                        if (lane < dd) xcur[lane] = xmeas[lane];
+                        __syncwarp();
+                    } else {
+                        // model step through lift/proj (mpc.py:264-267): x+ = proj(f(lift(x), u))
+                        if (lane < a.nblk) {
+                            double phi = 1.0;
+                            if (lane > 0)
+                                for (int l = 0; l < M; ++l) {
+                                    const double ul = s.Uo[l];
+                                    for (int q = 0; q < pow[(lane - 1) * M + l]; ++q) phi *= ul;
+                                }
+                            s.scr[lane] = phi;
+                        }
+                        __syncwarp();
+                        const double fx = apply_A<CF>(model, s.scr, 0, s.x0, lane);
+                        __syncwarp();
+                        if (lane < N) s.va[lane] = fx;
+                        __syncwarp();
+                        proj_state<CF>(a.lift_mode, d, s.va, xcur, lane);
+                    }
+                    if (lane < dd) xs_k[(size_t)lane * (S + 1) + step + 1] = xcur[lane];
+                }
+
+                // shift the guesses (mpc.py:271-272) and, with them, the ADMM warm start
+                // (each lane moves its own component through time: no cross-lane hazard)
+                if (lane < N)
+                    for (int t = 0; t < H; ++t) s.Xg[t * N + lane] = s.Xg[(t + 1) * N + lane];
+                if (lane < M)
+                    for (int t = 0; t + 1 < H; ++t) {
+                        s.Ug[t * M + lane] = s.Ug[(t + 1) * M + lane];
+                        s.z[t * M + lane] = s.z[(t + 1) * M + lane];
+                        s.y[t * M + lane] = s.y[(t + 1) * M + lane];
+                    }
+                __syncwarp();
+
+                // built-in exit condition: infidelity of the new plant state below a threshold (mpc.py:289-292)
+                if (!a.external_plant && a.exit_infid > 0.0 && a.fid_vec) {
+                    double f = 0.0;
+                    if (lane < dd) {
+                        const double2 w = a.fid_vec[lane], x = xcur[lane];
+                        f = w.x * x.x + w.y * x.y;
+                    }
+                    f = warp_sum(f);
+                    if (1.0 - f < a.exit_infid) {
+                        exit_code = 1;
+                        ++step;
+                        break;
+                    }
+                }
+            }
+        }
+
+        // ---- results
+        if (lane == 0) {
+            a.exit_code[k] = exit_code;
+            a.steps_done[k] = step;
+            if (a.counters) {
+                int *c = a.counters + (size_t)k * 4;
+                if (a.step_begin == 0) c[0] = c[1] = c[2] = c[3] = 0;
+                c[0] += cnt.admm;
+                c[1] += cnt.factor;
+                c[2] += cnt.polish;
+                c[3] += cnt.solves;
+            }
+        }
+        if (a.fidelity && !a.external_plant && a.fid_vec) {
+            double f = 0.0;
+            if (lane < dd) {
+                const double2 w = a.fid_vec[lane], x = xcur[lane];
+                f = w.x * x.x + w.y * x.y;
+            }
+            f = warp_sum(f);
+            if (lane == 0) a.fidelity[k] = f;
+        }
+        if (a.state) {
+            double *st = a.state + (size_t)k * persist;
+            int o = 0;
+            for (int e = lane; e < (H + 1) * N; e += 32) st[o + e] = s.Xg[e];
+            o += (H + 1) * N;
+            for (int e = lane; e < H * M; e += 32) {
+                st[o + e] = s.Ug[e];
+                st[o + H * M + e] = s.z[e];
+                st[o + 2 * H * M + e] = s.y[e];
+            }
+            o += 3 * H * M;
+            if (lane < xdim) {
+                st[o + 2 * lane] = xmeas[lane].x;
+                st[o + 2 * lane + 1] = xmeas[lane].y;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone horizon QP: one warp per instance, dense per-stage operators read from global memory.
+// Workspace per instance (doubles): Q [(H+1) N N] | R [H M M] | r [(H+1) N] | qlin [(H+1) N] | ub [H M] | Rub [H M]
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ inline long long qp_ws_doubles(int N, int M, int H) {
+    return (long long)(H + 1) * N * N + (long long)H * M * M + 2LL * (H + 1) * N + 2LL * H * M;
+}
+
+struct QpArgs {
+    long long n_inst;
+    int H, has_du, has_uprev;
+    double sat, du;
+    QPSet set;
+    const double2 *x_init, *X_bm, *Q_ls, *A_ls, *B_ls, *D_ls;
+    const double *U_bm, *R_ls, *u_prev;
+    double2 *X_out;
+    double *U_out, *obj_out;
+    int *status_out, *iters_out;
+    double *ws;
+    int slab_doubles;
+};
+
+template <class CF>
+__global__ void __launch_bounds__(512) qp_kernel(const QpArgs a) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    extern __shared__ double2 smem2[];
+    double *smem = reinterpret_cast<double *>(smem2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int H = a.H;
+    Slab<CF> s;
+    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, 1, C);
+
+    for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
+        double *ws = a.ws + k * qp_ws_doubles(N, M, H);
+        double *wQ = ws, *wR = wQ + (size_t)(H + 1) * N * N, *wr = wR + H * M * M, *wql = wr + (H + 1) * N,
+               *wub = wql + (H + 1) * N, *wRub = wub + H * M;
+        const double2 *Qk = a.Q_ls + (size_t)k * (H + 1) * C * C;
+        const double *Rk = a.R_ls + (size_t)k * H * M * M;
+        const double2 *Xb = a.X_bm + (size_t)k * C * (H + 1);
+        const double *Ub = a.U_bm + (size_t)k * M * H;
+        // ---- realify the instance (optimize.py:21-35)
+        for (int e = lane; e < (H + 1) * N * N; e += 32) {
+            const int t = e / (N * N), ij = e % (N * N);
+            wQ[e] = realified_sym(Qk + (size_t)t * C * C, C, ij / N, ij % N);
+        }
+        for (int e = lane; e < H * M * M; e += 32) {
+            const int t = e / (M * M), ij = e % (M * M);
+            wR[e] = 0.5 * (Rk[t * M * M + ij] + Rk[t * M * M + (ij % M) * M + ij / M]);
+        }
+        for (int e = lane; e < (H + 1) * N; e += 32) {
+            const int t = e / N, kk = e % N;
+            const double2 v = Xb[(kk % C) * (H + 1) + t];
+            wr[e] = kk < C ? v.x : v.y;
+        }
+        for (int e = lane; e < H * M; e += 32) wub[e] = Ub[(e % M) * H + e / M];
+        __syncwarp();
+        for (int e = lane; e < (H + 1) * N; e += 32) {
+            const int t = e / N, kk = e % N;
+            double acc = 0.0;
+            for (int j = 0; j < N; ++j) acc = fma(wQ[(size_t)t * N * N + kk * N + j], wr[t * N + j], acc);
+            wql[e] = acc;
+        }
+        for (int e = lane; e < H * M; e += 32) {
+            const int t = e / M, i = e % M;
+            double acc = 0.0;
+            for (int j = 0; j < M; ++j) acc = fma(wR[t * M * M + i * M + j], wub[t * M + j], acc);
+            wRub[e] = acc;
+        }
+        // ---- slab: B, D, x0, bounds, cold ADMM start
+        const double2 *Bk = a.B_ls + (size_t)k * H * C * M;
+        const double2 *Dk = a.D_ls + (size_t)k * H * C;
+        for (int e = lane; e < H * N * M; e += 32) {
+            const int t = e / (N * M), rem = e % (N * M), kk = rem / M, i = rem % M;
+            const double2 v = Bk[((size_t)t * C + kk % C) * M + i];
+            s.B[e] = kk < C ? v.x : v.y;
+        }
+        for (int e = lane; e < H * N; e += 32) {
+            const int t = e / N, kk = e % N;
+            const double2 v = Dk[(size_t)t * C + kk % C];
+            s.D[e] = kk < C ? v.x : v.y;
+        }
+        for (int e = lane; e < H; e += 32) s.phi[e] = 1.0;
+        for (int e = lane; e < H * M; e += 32) {
+            s.z[e] = 0.0;
+            s.y[e] = 0.0;
+        }
+        if (lane < C) {
+            const double2 v = a.x_init[(size_t)k * C + lane];
+            s.x0[lane] = v.x;
+            s.x0[C + lane] = v.y;
+        }
+        if (lane < M) {
+            double lo = -a.sat, hi = a.sat;
+            if (a.has_du && a.has_uprev) {   // optimize.py:29-30
+                const double up = a.u_prev[(size_t)k * M + lane];
+                lo = fmax(lo, up - a.du);
+                hi = fmin(hi, up + a.du);
+            }
+            s.lo0[lane] = lo;
+            s.hi0[lane] = hi;
+        }
+        __syncwarp();
+
+        StageOps ops;
+        ops.blocks = a.A_ls + (size_t)k * H * C * C;
+        ops.nblk = 1;
+        ops.stage_stride = C * C;
+        QPData qp;
+        qp.Q = wQ;
+        qp.q_stride = N * N;
+        qp.Qf = wQ + (size_t)H * N * N;
+        qp.R = wR;
+        qp.r_stride = M * M;
+        qp.r = wr;
+        qp.qlin = wql;
+        qp.qlinf = wql + H * N;
+        qp.ub = wub;
+        qp.Rub = wRub;
+        qp.sat = a.sat;
+        qp.q_diag = 0;
+        Counters cnt = {0, 0, 0, 0};
+        int status = qp_solve<CF>(s, ops, qp, a.set, H, lane, cnt);
+        const double obj = qp_objective<CF>(s, qp, H, lane);
+        if (!isfinite(obj)) status = 3;   // mpc.py:200
+        double2 *Xo = a.X_out + (size_t)k * C * (H + 1);
+        double *Uo = a.U_out + (size_t)k * M * H;
+        for (int e = lane; e < C * (H + 1); e += 32) {
+            const int kk = e / (H + 1), t = e % (H + 1);
+            Xo[e] = make_double2(s.Xo[t * N + kk], s.Xo[t * N + C + kk]);
+        }
+        for (int e = lane; e < M * H; e += 32) Uo[e] = s.Uo[(e % H) * M + e / H];
+        if (lane == 0) {
+            a.obj_out[k] = obj;
+            a.status_out[k] = status;
+            if (a.iters_out) {
+                a.iters_out[2 * k] = cnt.admm;
+                a.iters_out[2 * k + 1] = cnt.factor;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone linearisation (linearize.py:61-70)
+// ---------------------------------------------------------------------------------------------------------
+struct LinArgs {
+    long long n_inst;
+    int H, nblk;
+    const double2 *A_blocks;
+    const int *powers;
+    const double2 *Xg;
+    const double *Ug;
+    double2 *A_out, *B_out, *D_out;
+    int slab_doubles;
+};
+
+template <class CF>
+__global__ void __launch_bounds__(512) linearize_kernel(const LinArgs a) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    extern __shared__ double2 smem2[];
+    double *smem = reinterpret_cast<double *>(smem2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int H = a.H;
+    Slab<CF> s;
+    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, a.nblk, C);
+    StageOps model;
+    model.blocks = a.A_blocks;
+    model.nblk = a.nblk;
+    model.stage_stride = 0;
+    for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
+        const double2 *Xk = a.Xg + (size_t)k * C * (H + 1);
+        const double *Uk = a.Ug + (size_t)k * M * H;
+        for (int e = lane; e < (H + 1) * N; e += 32) {
+            const int t = e / N, kk = e % N;
+            const double2 v = Xk[(kk % C) * (H + 1) + t];
+            s.Xg[e] = kk < C ? v.x : v.y;
+        }
+        for (int e = lane; e < H * M; e += 32) s.Ug[e] = Uk[(e % M) * H + e / M];
+        __syncwarp();
+        linearize<CF>(s, model, a.powers, H, lane);
+        double2 *Ao = a.A_out + (size_t)k * H * C * C;
+        double2 *Bo = a.B_out + (size_t)k * H * C * M;
+        double2 *Do = a.D_out + (size_t)k * H * C;
+        for (int e = lane; e < H * C * C; e += 32) {
+            const int t = e / (C * C), ij = e % (C * C);
+            double2 acc = make_double2(0.0, 0.0);
+            for (int kb = 0; kb < a.nblk; ++kb) {
+                const double2 v = a.A_blocks[kb * C * C + ij];
+                const double ph = s.phi[t * a.nblk + kb];
+                acc.x = fma(ph, v.x, acc.x);
+                acc.y = fma(ph, v.y, acc.y);
+            }
+            Ao[e] = acc;
+        }
+        for (int e = lane; e < H * C * M; e += 32) {
+            const int t = e / (C * M), rem = e % (C * M), r = rem / M, i = rem % M;
+            Bo[e] = make_double2(s.B[(t * N + r) * M + i], s.B[(t * N + C + r) * M + i]);
+        }
+        for (int e = lane; e < H * C; e += 32) {
+            const int t = e / C, r = e % C;
+            Do[e] = make_double2(s.D[t * N + r], s.D[t * N + C + r]);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stand-alone line search (mpc.py:101-125); costs and references shared by all instances.
+// Workspace (doubles): Q [(H+1) N N] | R [H M M] | r [(H+1) N] | ub [H M]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void line_search_prep(int C, int M, int H, const double2 *Q_ls, const double *R_ls, const double2 *X_ref,
+                                 const double *U_ref, double *ws) {
+    const int N = 2 * C;
+    double *wQ = ws, *wR = wQ + (size_t)(H + 1) * N * N, *wr = wR + H * M * M, *wub = wr + (H + 1) * N;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int e = tid; e < (H + 1) * N * N; e += nt) {
+        const int t = e / (N * N), ij = e % (N * N);
+        wQ[e] = realified_sym(Q_ls + (size_t)t * C * C, C, ij / N, ij % N);
+    }
+    for (int e = tid; e < H * M * M; e += nt) {
+        const int t = e / (M * M), ij = e % (M * M);
+        wR[e] = 0.5 * (R_ls[t * M * M + ij] + R_ls[t * M * M + (ij % M) * M + ij / M]);
+    }
+    for (int e = tid; e < (H + 1) * N; e += nt) {
+        const int t = e / N, kk = e % N;
+        const double2 v = X_ref[(kk % C) * (H + 1) + t];
+        wr[e] = kk < C ? v.x : v.y;
+    }
+    for (int e = tid; e < H * M; e += nt) wub[e] = U_ref[(e % M) * H + e / M];
+}
+
+struct LsArgs {
+    long long n_inst;
+    int H;
+    const double2 *Xg, *Xo;
+    const double *Ug, *Uo;
+    double *alpha_out, *step_out;
+    const double *ws;
+    int slab_doubles;
+};
+
+template <class CF>
+__global__ void __launch_bounds__(512) line_search_kernel(const LsArgs a) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    extern __shared__ double2 smem2[];
+    double *smem = reinterpret_cast<double *>(smem2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int H = a.H;
+    Slab<CF> s;
+    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, 1, C);
+    QPData qp;
+    qp.Q = a.ws;
+    qp.q_stride = N * N;
+    qp.Qf = a.ws + (size_t)H * N * N;
+    qp.R = a.ws + (size_t)(H + 1) * N * N;
+    qp.r_stride = M * M;
+    qp.r = qp.R + H * M * M;
+    qp.ub = qp.r + (H + 1) * N;
+    qp.qlin = qp.qlinf = qp.Rub = nullptr;
+    qp.sat = 0.0;
+    qp.q_diag = 0;
+    for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
+        const double2 *Xgk = a.Xg + (size_t)k * C * (H + 1), *Xok = a.Xo + (size_t)k * C * (H + 1);
+        const double *Ugk = a.Ug + (size_t)k * M * H, *Uok = a.Uo + (size_t)k * M * H;
+        for (int e = lane; e < (H + 1) * N; e += 32) {
+            const int t = e / N, kk = e % N;
+            const double2 g = Xgk[(kk % C) * (H + 1) + t], o = Xok[(kk % C) * (H + 1) + t];
+            s.Xg[e] = kk < C ? g.x : g.y;
+            s.Xo[e] = kk < C ? o.x : o.y;
+        }
+        for (int e = lane; e < H * M; e += 32) {
+            s.Ug[e] = Ugk[(e % M) * H + e / M];
+            s.Uo[e] = Uok[(e % M) * H + e / M];
+        }
+        __syncwarp();
+        double alpha, stp;
+        line_search<CF>(s, qp, H, lane, alpha, stp);
+        if (lane == 0) {
+            a.alpha_out[k] = alpha;
+            a.step_out[k] = stp;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plant step(s) (experiment.py:202-212): one warp per member, d <= 5
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expm_step_kernel(long long n, int d, int m, int n_seg, double dt, const double2 *H0,
+                                                        const double2 *H1, int shared_ham, const double *u,
+                                                        const double2 *rho_in, double2 *rho_out, double2 *prop_out) {
+    extern __shared__ double2 smem2[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int dd = d * d;
+    double2 *base = smem2 + (size_t)warp * 5 * dd;
+    double2 *rho = base, *Hm = base + dd, *G = base + 2 * dd, *T0 = base + 3 * dd, *T1 = base + 4 * dd;
+    for (long long k = (long long)blockIdx.x * wpc + warp; k < n; k += (long long)gridDim.x * wpc) {
+        const double2 *H0k = H0 + (shared_ham ? 0 : (size_t)k * dd);
+        const double2 *H1k = H1 + (shared_ham ? 0 : (size_t)k * m * dd);
+        if (lane < dd) rho[lane] = rho_in[(size_t)k * dd + lane];
+        __syncwarp();
+        for (int sgm = 0; sgm < n_seg; ++sgm) {
+            if (lane < dd) {
+                double2 h = H0k[lane];
+                for (int i = 0; i < m; ++i) {
+                    const double uu = u[((size_t)k * n_seg + sgm) * m + i];
+                    const double2 h1 = H1k[i * dd + lane];
+                    h.x = fma(uu, h1.x, h.x);
+                    h.y = fma(uu, h1.y, h.y);
+                }
+                Hm[lane] = h;
+            }
+            __syncwarp();
+            expm_minus_i(Hm, dt, d, G, T0, T1, lane);
+            if (prop_out && lane < dd) prop_out[((size_t)k * n_seg + sgm) * dd + lane] = T0[lane];
+            conjugate(rho, T0, d, G, lane);
+            if (lane < dd) rho_out[((size_t)k * n_seg + sgm) * dd + lane] = rho[lane];
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Taylor discretisation (vectorize.py:8-49): one CTA per member.  Recurrence on word length: the sum of all
+// words of length k with control-exponent tuple e is W_k[e] = sum_j W_{k-1}[e - 1_j] L_j  (1_0 = 0).
+// smem: cur [p1][c*c] | nxt [p1][c*c] | acc [p1][c*c] complex, succ [p1][m+1] int
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, int order, int p1, double dt, const double2 *L,
+                                                     const int *powers, double2 *out) {
+    extern __shared__ double2 smem2[];
+    const int cc = c * c;
+    double2 *cur = smem2, *nxt = cur + (size_t)p1 * cc, *acc = nxt + (size_t)p1 * cc;
+    int *succ = reinterpret_cast<int *>(acc + (size_t)p1 * cc);   // succ[e][j]: index of powers[e] + 1_j, or -1
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < p1 * (m + 1); e += nt) {
+        const int src = e / (m + 1), j = e % (m + 1);
+        int found = -1;
+        if (j == 0) found = src;
+        else
+            for (int q = 0; q < p1 && found < 0; ++q) {
+                bool same = true;
+                for (int l = 0; l < m; ++l) same &= powers[q * m + l] == powers[src * m + l] + (l == j - 1 ? 1 : 0);
+                if (same) found = q;
+            }
+        succ[e] = found;
+    }
+    __syncthreads();
+    for (long long k = blockIdx.x; k < n; k += gridDim.x) {
+        const double2 *Lk = L + (size_t)k * (m + 1) * cc;
+        // constant row is the all-zero exponent tuple: find it (row 0 in the reference's ordering)
+        for (int e = tid; e < p1 * cc; e += nt) {
+            const int blk = e / cc, ij = e % cc;
+            bool zero = true;
+            for (int l = 0; l < m; ++l) zero &= powers[blk * m + l] == 0;
+            const double2 v = make_double2((zero && ij / c == ij % c) ? 1.0 : 0.0, 0.0);
+            cur[e] = v;
+            acc[e] = v;
+        }
+        __syncthreads();
+        double pref = 1.0;
+        for (int ord = 1; ord <= order; ++ord) {
+            pref *= dt / (double)ord;
+            for (int e = tid; e < p1 * cc; e += nt) {
+                const int dst = e / cc, ij = e % cc, i = ij / c, jcol = ij % c;
+                double2 sum = make_double2(0.0, 0.0);
+                for (int src = 0; src < p1; ++src)
+                    for (int j = 0; j <= m; ++j) {
+                        if (succ[src * (m + 1) + j] != dst) continue;
+                        const double2 *W = cur + (size_t)src * cc + i * c;
+                        const double2 *Lj = Lk + (size_t)j * cc + jcol;
+                        for (int q = 0; q < c; ++q) sum = cfma(W[q], Lj[q * c], sum);
+                    }
+                nxt[e] = sum;
+            }
+            __syncthreads();
+            for (int e = tid; e < p1 * cc; e += nt) {
+                const double2 v = nxt[e];
+                cur[e] = v;
+                acc[e].x = fma(pref, v.x, acc[e].x);
+                acc[e].y = fma(pref, v.y, acc[e].y);
+            }
+            __syncthreads();
+        }
+        // hstack layout: out[i][blk*c + j]
+        double2 *ok = out + (size_t)k * c * c * p1;
+        for (int e = tid; e < p1 * cc; e += nt) {
+            const int blk = e / cc, ij = e % cc, i = ij / c, j = ij % c;
+            ok[(size_t)i * c * p1 + blk * c + j] = acc[e];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void hist_kernel(long long n, const double *f, double lo, double hi, int nbins, unsigned long long *counts) {
+    const double scale = nbins / (hi - lo);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = f[i];
+        if (!(v == v)) continue;
+        int b = (int)floor((v - lo) * scale);
+        b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
+        atomicAdd(&counts[b], 1ULL);
+    }
+}
+
+// register-resident fp64 FMA chains: the denominator of the fp64 roofline, measured on the same part
+__global__ void __launch_bounds__(256) fp64_fma_kernel(long long iters, double seed, double *out) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + i + threadIdx.x * 1e-9;
+    const double m = 1.0 - 1e-12, c = 1e-13;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += a[i];
+    if (sum == 123.456) out[0] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Launch geometry
+// ---------------------------------------------------------------------------------------------------------
+struct Geometry {
+    int warps, ctas, smem, slab_doubles, shared_doubles;
+};
+
+static int device_props(int *sms, int *max_smem) {
+    int dev = 0;
+    M4Q_CUDA(cudaGetDevice(&dev));
+    M4Q_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    M4Q_CUDA(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+// warps per CTA: as many slabs as fit in shared memory (<= 16), grid = SMs * resident CTAs
+template <class KernelT>
+static int plan(KernelT kernel, int slab_doubles, int shared_doubles, long long n_units, bool have_device, Geometry *g) {
+    int sms = 148, max_smem = 232448;
+    if (have_device && device_props(&sms, &max_smem) != 0) return -1;
+    const long long slab_b = (long long)slab_doubles * 8, shared_b = (long long)shared_doubles * 8;
+    if (shared_b + slab_b > max_smem) return fail("horizon too long for the shared-memory slab of this (c, m) instantiation");
+    int warps = (int)((max_smem - shared_b) / slab_b);
+    if (warps > 16) warps = 16;
+    // small slabs: prefer several CTAs per SM over one wide CTA so that the CTA-shared tables stay cheap to load
+    g->warps = warps;
+    g->smem = (int)(shared_b + (long long)warps * slab_b);
+    g->slab_doubles = slab_doubles;
+    g->shared_doubles = shared_doubles;
+    int per_sm = 1;
+    if (have_device) {
+        M4Q_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem));
+        M4Q_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, g->smem));
+        if (per_sm < 1) return fail("kernel does not fit on an SM (registers x threads)");
+    } else {
+        per_sm = (int)(max_smem / (g->smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long ctas = (long long)sms * per_sm;
+    const long long need = (n_units + warps - 1) / warps;
+    if (need < ctas) ctas = need < 1 ? 1 : need;
+    g->ctas = (int)ctas;
+    return 0;
+}
+
+static QPSet qp_settings(const m4q_qp_settings *s) {
+    QPSet q;
+    q.rho = (s && s->rho > 0) ? s->rho : 0.1;
+    q.alpha = (s && s->alpha > 0) ? s->alpha : 1.6;
+    q.polish = s ? s->polish : 1;
+    q.eps = (s && s->eps > 0) ? s->eps : (q.polish ? 1e-2 : 1e-5);
+    q.max_admm = (s && s->max_admm > 0) ? s->max_admm : 400;
+    q.max_polish = (s && s->max_polish > 0) ? s->max_polish : 8;
+    return q;
+}
+
+template <class CF> static int mpc_shared_doubles(int nblk) {
+    return 2 * nblk * CF::C * CF::C + 2 * CF::N * CF::N + rup(CF::M * CF::M, 2) + rup(cdiv(nblk * CF::M, 2) + 1, 2);
+}
+
+template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
+    const int dd = p->d * p->d;
+    const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2);
+    return plan(mpc_kernel<CF>, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
+}
+
+template <class CF>
+static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base, cudaStream_t st) {
+    Geometry g;
+    if (mpc_geometry<CF>(p, n, true, &g) != 0) return -1;
+    MpcArgs a = base;
+    a.slab_doubles = g.slab_doubles;
+    a.shared_doubles = g.shared_doubles;
+    build_tables<<<1, 256, 0, st>>>(CF::C, CF::M, p->n_targ, reinterpret_cast<const double2 *>(p->Q),
+                                    reinterpret_cast<const double2 *>(p->Qf), p->R,
+                                    reinterpret_cast<const double2 *>(p->X_targ), p->U_targ, a.tab);
+    M4Q_CUDA(cudaGetLastError());
+    mpc_kernel<CF><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define M4Q_DISPATCH(c, m, ...)                                                       \
+    do {                                                                              \
+        if ((c) == 4 && (m) == 1) { using CF = Cfg<4, 1>; __VA_ARGS__; }              \
+        else if ((c) == 4 && (m) == 2) { using CF = Cfg<4, 2>; __VA_ARGS__; }         \
+        else if ((c) == 9 && (m) == 2) { using CF = Cfg<9, 2>; __VA_ARGS__; }         \
+        else if ((c) == 8 && (m) == 2) { using CF = Cfg<8, 2>; __VA_ARGS__; }         \
+        else if ((c) == 16 && (m) == 3) { using CF = Cfg<16, 3>; __VA_ARGS__; }       \
+        else return fail("unsupported (c, m): no compiled instantiation");            \
+    } while (0)
+
+static bool supported(int c, int m) {
+    return (c == 4 && m == 1) || (c == 4 && m == 2) || (c == 9 && m == 2) || (c == 8 && m == 2) || (c == 16 && m == 3);
+}
+
+static int check_problem(const m4q_mpc_problem *p) {
+    if (!p) return fail("null problem");
+    if (!supported(p->c, p->m)) return fail("unsupported (c, m): no compiled instantiation");
+    if (p->p < 1 || p->p + 1 > MAXBLK) return fail("number of monomial blocks out of range");
+    if (p->horizon < 1 || p->n_steps < 1 || p->measure_freq < 1) return fail("horizon, n_steps and measure_freq must be >= 1");
+    if (p->n_targ < p->n_steps + p->horizon) return fail("X_targ needs at least n_steps + horizon columns");
+    if (p->d < 1 || p->d * p->d > 32) return fail("plant dimension out of range (d*d <= 32)");
+    if (p->lift_mode == M4Q_LIFT_IDENTITY && p->d * p->d != p->c) return fail("identity lift needs d*d == c");
+    if (p->lift_mode == M4Q_LIFT_COUPLED && !((p->d == 4 && p->c == 8) || (p->d == 9 && p->c == 18)))
+        return fail("coupled lift needs d = dA^2 and c = 2 dA^2");
+    if (p->lift_mode == M4Q_LIFT_TRUNC32 && !(p->d == 3 && p->c == 4)) return fail("trunc32 lift needs d = 3, c = 4");
+    if (p->lift_mode == M4Q_LIFT_TRUNC32 && p->measure_freq != 1)
+        return fail("QExperiment32.proj is not a map back to the plant space (experiment.py:232-235); measure_freq must be 1");
+    if (!(p->sat > 0)) return fail("sat is mandatory (optimize.py:43)");
+    return 0;
+}
+
+}  // namespace m4q
+
+using namespace m4q;
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int m4q_version(void) { return M4Q_VERSION; }
+
+const char *m4q_last_error(void) { return g_err.c_str(); }
+
+int m4q_supported(int32_t c, int32_t m) { return supported(c, m) ? 1 : 0; }
+
+int m4q_expm_step_batched(int64_t N, int32_t d, int32_t m, int32_t n_seg, double dt, const double *H0, const double *H1,
+                          int32_t shared_hamiltonian, const double *u, const double *rho_in, double *rho_out,
+                          double *prop_out, void *stream) {
+    if (N <= 0) return 0;
+    if (d < 1 || d * d > 32) return fail("plant dimension out of range (d*d <= 32)");
+    if (!H0 || !H1 || !u || !rho_in || !rho_out) return fail("null pointer");
+    const int wpc = 8;
+    long long ctas = (N + wpc - 1) / wpc;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    const size_t smem = (size_t)wpc * 5 * d * d * sizeof(double2);
+    expm_step_kernel<<<(int)ctas, wpc * 32, smem, (cudaStream_t)stream>>>(
+        N, d, m, n_seg, dt, (const double2 *)H0, (const double2 *)H1, shared_hamiltonian, u, (const double2 *)rho_in,
+        (double2 *)rho_out, (double2 *)prop_out);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int m4q_taylor_discretize_batched(int64_t N, int32_t c, int32_t m, int32_t order, int32_t p1, double dt, const double *L,
+                                  const int32_t *powers, double *out, void *stream) {
+    if (N <= 0) return 0;
+    if (!L || !powers || !out) return fail("null pointer");
+    const size_t smem = (size_t)3 * p1 * c * c * sizeof(double2) + (size_t)p1 * (m + 1) * sizeof(int);
+    if (smem > 227 * 1024) return fail("model too large for the shared-memory discretisation kernel");
+    M4Q_CUDA(cudaFuncSetAttribute(taylor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = N > 148 * 4 ? 148 * 4 : N;
+    taylor_kernel<<<(int)ctas, 128, smem, (cudaStream_t)stream>>>(N, c, m, order, p1, dt, (const double2 *)L, powers,
+                                                                 (double2 *)out);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H, const double *A_blocks,
+                          const int32_t *powers, const double *Xg, const double *Ug, double *A_out, double *B_out,
+                          double *D_out, void *stream) {
+    if (N <= 0) return 0;
+    if (p < 1 || p + 1 > MAXBLK) return fail("number of monomial blocks out of range");
+    LinArgs a;
+    a.n_inst = N;
+    a.H = H;
+    a.nblk = p + 1;
+    a.A_blocks = (const double2 *)A_blocks;
+    a.powers = powers;
+    a.Xg = (const double2 *)Xg;
+    a.Ug = Ug;
+    a.A_out = (double2 *)A_out;
+    a.B_out = (double2 *)B_out;
+    a.D_out = (double2 *)D_out;
+    M4Q_DISPATCH(c, m, {
+        Geometry g;
+        const int slab = rup(Slab<CF>::doubles(H, p + 1, CF::C), 2);
+        if (plan(linearize_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        a.slab_doubles = slab;
+        linearize_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
+    });
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int64_t m4q_qp_workspace_bytes(int64_t N, int32_t c, int32_t m, int32_t H) {
+    return (int64_t)sizeof(double) * N * qp_ws_doubles(2 * c, m, H);
+}
+
+int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double *x_init, const double *X_bm,
+                        const double *U_bm, const double *Q_ls, const double *R_ls, const double *A_ls, const double *B_ls,
+                        const double *D_ls, const double *u_prev, double sat, double du, int32_t has_du,
+                        const m4q_qp_settings *settings_host, double *X_out, double *U_out, double *obj_out,
+                        int32_t *status_out, int32_t *iters_out, void *workspace, void *stream) {
+    if (N <= 0) return 0;
+    if (!(sat > 0)) return fail("sat is mandatory (optimize.py:43)");
+    if (!workspace) return fail("null workspace");
+    QpArgs a;
+    a.n_inst = N;
+    a.H = H;
+    a.has_du = has_du;
+    a.has_uprev = u_prev != nullptr;
+    a.sat = sat;
+    a.du = du;
+    a.set = qp_settings(settings_host);
+    a.x_init = (const double2 *)x_init;
+    a.X_bm = (const double2 *)X_bm;
+    a.Q_ls = (const double2 *)Q_ls;
+    a.A_ls = (const double2 *)A_ls;
+    a.B_ls = (const double2 *)B_ls;
+    a.D_ls = (const double2 *)D_ls;
+    a.U_bm = U_bm;
+    a.R_ls = R_ls;
+    a.u_prev = u_prev;
+    a.X_out = (double2 *)X_out;
+    a.U_out = U_out;
+    a.obj_out = obj_out;
+    a.status_out = status_out;
+    a.iters_out = iters_out;
+    a.ws = (double *)workspace;
+    M4Q_DISPATCH(c, m, {
+        Geometry g;
+        const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
+        if (plan(qp_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        a.slab_doubles = slab;
+        qp_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
+    });
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int64_t m4q_line_search_workspace_bytes(int32_t c, int32_t m, int32_t H) {
+    const int N = 2 * c;
+    return (int64_t)sizeof(double) * ((int64_t)(H + 1) * N * N + (int64_t)H * m * m + (int64_t)(H + 1) * N + (int64_t)H * m);
+}
+
+int m4q_line_search_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double *Q_ls, const double *R_ls,
+                            const double *X_ref, const double *U_ref, const double *Xg, const double *Ug, const double *Xo,
+                            const double *Uo, double *alpha_out, double *step_out, void *workspace, void *stream) {
+    if (N <= 0) return 0;
+    if (!workspace) return fail("null workspace");
+    line_search_prep<<<32, 256, 0, (cudaStream_t)stream>>>(c, m, H, (const double2 *)Q_ls, R_ls, (const double2 *)X_ref, U_ref,
+                                                          (double *)workspace);
+    M4Q_CUDA(cudaGetLastError());
+    LsArgs a;
+    a.n_inst = N;
+    a.H = H;
+    a.Xg = (const double2 *)Xg;
+    a.Xo = (const double2 *)Xo;
+    a.Ug = Ug;
+    a.Uo = Uo;
+    a.alpha_out = alpha_out;
+    a.step_out = step_out;
+    a.ws = (const double *)workspace;
+    M4Q_DISPATCH(c, m, {
+        Geometry g;
+        const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
+        if (plan(line_search_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        a.slab_doubles = slab;
+        line_search_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
+    });
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int64_t m4q_mpc_state_bytes(const m4q_mpc_problem *p, int64_t N) {
+    if (check_problem(p) != 0) return -1;
+    int persist = 0;
+    const int dd = p->d * p->d;
+    M4Q_DISPATCH(p->c, p->m, { persist = Slab<CF>::persistent_doubles(p->horizon, cmax(dd, CF::C)); });
+    return (int64_t)sizeof(double) * N * persist;
+}
+
+int64_t m4q_mpc_table_bytes(const m4q_mpc_problem *p) {
+    if (check_problem(p) != 0) return -1;
+    return (int64_t)sizeof(double) * TableLayout(2 * p->c, p->m, p->n_targ).total;
+}
+
+int m4q_mpc_launch_info(const m4q_mpc_problem *p, int32_t *warps_per_cta, int32_t *ctas, int32_t *smem_bytes) {
+    if (check_problem(p) != 0) return -1;
+    Geometry g;
+    int count = 0;
+    const bool have_device = cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+    if (!have_device) cudaGetLastError();
+    M4Q_DISPATCH(p->c, p->m, {
+        if (mpc_geometry<CF>(p, 1LL << 40, have_device, &g) != 0) return -1;
+    });
+    if (warps_per_cta) *warps_per_cta = g.warps;
+    if (ctas) *ctas = g.ctas;
+    if (smem_bytes) *smem_bytes = g.smem;
+    return 0;
+}
+
+int m4q_mpc_closed_loop(const m4q_mpc_problem *p, int64_t N, const double *x0, int32_t x0_shared, const double *H0,
+                        const double *H1, int32_t shared_hamiltonian, int32_t step_begin, int32_t step_end,
+                        int32_t external_plant, double *xs, double *us, int32_t *exit_code, int32_t *steps_done,
+                        int32_t *qp_count, int32_t *counters, double *fidelity, void *state, void *tables, void *stream) {
+    if (check_problem(p) != 0) return -1;
+    if (N <= 0) return 0;
+    if (!x0 || !xs || !us || !exit_code || !steps_done || !qp_count || !tables) return fail("null pointer");
+    if (!external_plant && (!H0 || !H1)) return fail("plant Hamiltonians are required unless external_plant is set");
+    if (step_begin < 0 || step_end > p->n_steps || step_begin >= step_end) return fail("bad step range");
+    if ((step_begin > 0 || step_end < p->n_steps) && !state) return fail("a partial step range needs the state buffer");
+    MpcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = p->horizon;
+    a.S = p->n_steps;
+    a.mf = p->measure_freq;
+    a.warm_start = p->warm_start;
+    a.max_iter = p->max_iter > 0 ? p->max_iter : 100;
+    a.lift_mode = p->lift_mode;
+    a.has_du = p->has_du;
+    a.n_targ = p->n_targ;
+    a.d = p->d;
+    a.nblk = p->p + 1;
+    a.dt = p->dt;
+    a.sat = p->sat;
+    a.du = p->du;
+    a.exit_infid = p->exit_infidelity;
+    a.set = qp_settings(&p->qp);
+    a.A_blocks = (const double2 *)p->A_blocks;
+    a.powers = p->powers;
+    a.fid_vec = (const double2 *)p->fid_vec;
+    a.tab = (double *)tables;
+    a.n_members = N;
+    a.x0 = (const double2 *)x0;
+    a.x0_shared = x0_shared;
+    a.H0 = (const double2 *)H0;
+    a.H1 = (const double2 *)H1;
+    a.shared_ham = shared_hamiltonian;
+    a.step_begin = step_begin;
+    a.step_end = step_end;
+    a.external_plant = external_plant;
+    a.xs = (double2 *)xs;
+    a.us = us;
+    a.exit_code = exit_code;
+    a.steps_done = steps_done;
+    a.qp_count = qp_count;
+    a.counters = counters;
+    a.fidelity = fidelity;
+    a.state = (double *)state;
+    M4Q_DISPATCH(p->c, p->m, { return launch_mpc<CF>(p, N, a, (cudaStream_t)stream); });
+    return 0;
+}
+
+int m4q_hist_fidelity(int64_t N, const double *fidelity, double lo, double hi, int32_t nbins, int64_t *counts, void *stream) {
+    if (N <= 0) return 0;
+    if (!(hi > lo) || nbins < 1) return fail("bad histogram range");
+    long long ctas = (N + 255) / 256;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    hist_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>(N, fidelity, lo, hi, nbins, (unsigned long long *)counts);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int m4q_fp64_fma_probe(int32_t ctas, int64_t iters, double *scratch, void *stream) {
+    fp64_fma_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(iters, 0.5, scratch);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
