@@ -48,7 +48,7 @@ typedef struct {
     int32_t c;             /* complex model-state dimension dim_x                               */
     int32_t m;             /* number of controls dim_u                                           */
     int32_t p;             /* number of control monomials (model.py:95-103: A = [A_x | A_u])     */
-    int32_t d;             /* plant Hilbert-space dimension (plant state is d*d complex)         */
+    int32_t d;             /* plant Hilbert-space dimension (plant state is d*d complex); 0 = external plant */
     int32_t horizon;       /* StepClock.horizon  (mpc.py:17)                                     */
     int32_t n_steps;       /* StepClock.n_steps  (mpc.py:18)                                     */
     int32_t measure_freq;  /* StepClock.measure_freq (mpc.py:19, :252)                           */
@@ -154,8 +154,9 @@ int m4q_line_search_batched(int64_t N, int32_t c, int32_t m, int32_t H,
  *   exit_code [N] int32; steps_done [N] int32; qp_count [N][S] int32 (QP solves per MPC step);
  *   counters [N][4] int32 (ADMM iterations, Riccati factorisations, polish rounds, QP solves);
  *   fidelity [N] f64 or NULL.
- *   external_plant != 0: the kernel does not propagate the plant; the caller writes xs[:, :, step+1] between
- *   launches (host-stepped mode for user-defined Experiment.simulate).
+ *   external_plant != 0 (with prob.d = 0): the kernel does not propagate the plant; xs is [N][c][S+1] and holds
+ *   LIFTED model states which the caller writes into xs[:, :, step_begin] before each single-step launch
+ *   (host-stepped mode for a user-defined Experiment.simulate / exit_condition; mpc.py:247-292 stay on the host).
  *   state: m4q_mpc_state_bytes(prob, N) bytes, carries guesses and ADMM duals between launches.
  */
 int64_t m4q_mpc_state_bytes(const m4q_mpc_problem *prob_host, int64_t N);

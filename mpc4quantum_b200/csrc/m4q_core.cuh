@@ -270,9 +270,11 @@ __device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPD
                                bool masked, int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q, LD = CF::LD;
     for (int e = lane; e < N * N; e += 32) s.P[e] = qp.Qf[e];
-    for (int e = lane; e < N * (LD - Q); e += 32) {   // zero the padding columns once
-        const int k = e / (LD - Q), j = Q + e % (LD - Q);
-        s.AB[k * LD + j] = 0.0;
+    if constexpr (LD > Q) {   // zero the padding columns once
+        for (int e = lane; e < N * (LD - Q); e += 32) {
+            const int k = e / (LD - Q), j = Q + e % (LD - Q);
+            s.AB[k * LD + j] = 0.0;
+        }
     }
     __syncwarp();
     for (int t = H - 1; t >= 0; --t) {

@@ -993,8 +993,9 @@ static int check_problem(const m4q_mpc_problem *p) {
     if (p->p < 1 || p->p + 1 > MAXBLK) return fail("number of monomial blocks out of range");
     if (p->horizon < 1 || p->n_steps < 1 || p->measure_freq < 1) return fail("horizon, n_steps and measure_freq must be >= 1");
     if (p->n_targ < p->n_steps + p->horizon) return fail("X_targ needs at least n_steps + horizon columns");
-    if (p->d < 1 || p->d * p->d > 32) return fail("plant dimension out of range (d*d <= 32)");
-    if (p->lift_mode == M4Q_LIFT_IDENTITY && p->d * p->d != p->c) return fail("identity lift needs d*d == c");
+    if (p->d < 0 || p->d * p->d > 32) return fail("plant dimension out of range (d*d <= 32)");
+    if (p->d == 0 && p->lift_mode != M4Q_LIFT_IDENTITY) return fail("d = 0 (external plant) goes with the identity lift");
+    if (p->d > 0 && p->lift_mode == M4Q_LIFT_IDENTITY && p->d * p->d != p->c) return fail("identity lift needs d*d == c");
     if (p->lift_mode == M4Q_LIFT_COUPLED && !((p->d == 4 && p->c == 8) || (p->d == 9 && p->c == 18)))
         return fail("coupled lift needs d = dA^2 and c = 2 dA^2");
     if (p->lift_mode == M4Q_LIFT_TRUNC32 && !(p->d == 3 && p->c == 4)) return fail("trunc32 lift needs d = 3, c = 4");
@@ -1193,6 +1194,7 @@ int m4q_mpc_closed_loop(const m4q_mpc_problem *p, int64_t N, const double *x0, i
     if (N <= 0) return 0;
     if (!x0 || !xs || !us || !exit_code || !steps_done || !qp_count || !tables) return fail("null pointer");
     if (!external_plant && (!H0 || !H1)) return fail("plant Hamiltonians are required unless external_plant is set");
+    if (!external_plant && p->d == 0) return fail("d = 0 is only valid with external_plant");
     if (step_begin < 0 || step_end > p->n_steps || step_begin >= step_end) return fail("bad step range");
     if ((step_begin > 0 || step_end < p->n_steps) && !state) return fail("a partial step range needs the state buffer");
     MpcArgs a;

@@ -1,0 +1,202 @@
+"""Plants ("experiments") -- API of mpc4quantum/experiment.py for the quantum classes on the MPC hot path.
+
+The reference integrates the von Neumann equation with qutip.mesolve under a piecewise-constant control
+(experiment.py:202-212, mpc.py:256-260).  Here each constant segment is the exact map rho <- U rho U^dagger with
+U = expm(-i (H0 + sum_k u_k H1_k) dt), evaluated by the sm_100a kernel behind ``m4q_expm_step_batched``.
+"""
+from abc import ABC, abstractmethod
+import math
+
+import numpy as np
+
+from . import _lib
+
+
+def _as_matrix(op):
+    return np.asarray(op.full() if hasattr(op, 'full') else op, dtype=complex)
+
+
+def isqrt(n):
+    """Integer square root (experiment.py:318-333)."""
+    if n < 0:
+        raise ValueError("Square root not defined for negative numbers.")
+    return math.isqrt(n)
+
+
+def split_blocks(bmatrix, nrows, ncols):
+    """Sub-blocks of a block matrix, row-major over blocks (experiment.py:309-315)."""
+    r, h = bmatrix.shape
+    return bmatrix.reshape(r // nrows, nrows, h // ncols, ncols).swapaxes(1, 2).reshape(-1, nrows, ncols)
+
+
+class Experiment(ABC):
+    """Interface of a controlled plant (experiment.py:8-49): f, lift, proj, simulate."""
+    lift_mode = _lib.LIFT_IDENTITY
+
+    def __init__(self):
+        self.ts = None
+        self.us = None
+        self.xs = None
+
+    @abstractmethod
+    def f(self, t, x, u):
+        """Time derivative of the state."""
+
+    @staticmethod
+    def lift(x):
+        return x
+
+    @staticmethod
+    def proj(z):
+        return z
+
+    @abstractmethod
+    def simulate(self, x0, ts, us):
+        """States at all times in ts, shape [dim, len(ts)], for a control function of time or an array [m, len(ts)]."""
+
+
+def _controls_on_grid(us, ts):
+    """Control per segment [n_seg, m]: us(ts[i]) for a callable (interp1d kind='previous'), column i otherwise."""
+    n_seg = len(ts) - 1
+    if callable(us):
+        cols = [np.real(np.asarray(us(ts[i]))).reshape(-1) for i in range(n_seg)]
+        return np.array(cols, dtype=float).reshape(n_seg, -1)
+    arr = np.atleast_2d(np.real(np.asarray(us)))
+    return np.ascontiguousarray(arr[:, :n_seg].T, dtype=float)
+
+
+def expm_segments(x0, H0, H1, u_seg, dt, shared=False, return_propagators=False):
+    """Batched plant propagation on the device.
+
+    x0 [N, d*d] complex, H0 [N, d, d] (or [d, d] with shared=True), H1 [N, m, d, d] (or [m, d, d]),
+    u_seg [N, n_seg, m] real -> device tensor [N, n_seg, d*d] of states after each segment (+ propagators).
+    """
+    lib = _lib.lib()
+    rho = _lib.dev(x0, np.complex128)
+    n, dd = rho.shape
+    d = isqrt(dd)
+    u = _lib.dev(u_seg, np.float64)
+    n_seg, m = u.shape[1], u.shape[2]
+    H0d = _lib.dev(H0, np.complex128)
+    H1d = _lib.dev(H1, np.complex128)
+    out = _lib.empty((n, n_seg, dd), np.complex128)
+    props = _lib.empty((n, n_seg, d, d), np.complex128) if return_propagators else None
+    _lib.check(lib.m4q_expm_step_batched(n, d, m, n_seg, float(dt), _lib.ptr(H0d), _lib.ptr(H1d), int(shared),
+                                         _lib.ptr(u), _lib.ptr(rho), _lib.ptr(out), _lib.ptr(props),
+                                         _lib.stream_ptr()))
+    return (out, props) if return_propagators else out
+
+
+class QExperiment(Experiment):
+    """Closed quantum system with Hamiltonian H0 + sum_k u_k(t) H1_k (experiment.py:175-212)."""
+
+    def __init__(self, H0, H1_list):
+        super().__init__()
+        self.H0 = _as_matrix(H0)
+        self.H1_list = [_as_matrix(h) for h in H1_list]
+        self._me_args = {}
+        self._sigma = 0
+
+    def f(self, t, x, u):
+        return self.H0 * x + np.sum([H1 * x * u1 for H1, u1 in zip(self.H1_list, u)], axis=0)
+
+    def set_sigma(self, sigma):
+        self._sigma = sigma
+
+    def set(self, key, value):
+        self._me_args[key] = value
+
+    def simulate(self, x0, ts, us):
+        ts = np.asarray(ts, dtype=float)
+        self.ts = ts
+        u_seg = _controls_on_grid(us, ts)
+        self.us = us
+        x = np.asarray(x0, dtype=complex).reshape(1, -1)
+        steps = np.diff(ts)
+        cols = [x[0]]
+        if len(steps) and np.allclose(steps, steps[0], rtol=1e-12, atol=0):
+            out = expm_segments(x, self.H0, np.stack(self.H1_list), u_seg[None], steps[0], shared=True)
+            cols += list(out[0].cpu().numpy())
+        else:
+            for i, h in enumerate(steps):
+                x = expm_segments(x, self.H0, np.stack(self.H1_list), u_seg[None, i:i + 1], h,
+                                  shared=True)[:, 0].cpu().numpy()
+                cols.append(x[0])
+        self.xs = np.array(cols).T
+        if self._sigma:
+            noise = np.random.randn(*self.xs.shape) + 1j * np.random.randn(*self.xs.shape)   # experiment.py:212
+            return self.xs + noise * self._sigma
+        return self.xs
+
+
+class QExperiment32(QExperiment):
+    """Qutrit plant observed in its qubit block (experiment.py:215-235)."""
+    lift_mode = _lib.LIFT_TRUNC32
+
+    @staticmethod
+    def lift(rho33_vec):
+        blk = np.asarray(rho33_vec, dtype=complex).reshape(3, 3)[:2, :2]
+        return (blk / np.linalg.svd(blk, compute_uv=False).sum()).flatten()    # Qobj.unit(): trace norm
+
+    @staticmethod
+    def proj(rho22_vec):
+        return np.asarray(rho22_vec).flatten()     # as the reference returns it (experiment.py:232-235)
+
+
+class QCoupledExperiment(QExperiment):
+    """Two identical subsystems observed through their reduced states (experiment.py:238-306)."""
+    lift_mode = _lib.LIFT_COUPLED
+
+    @staticmethod
+    def lift(rhoAB_vec):
+        dAB = isqrt(len(rhoAB_vec))
+        dA = isqrt(dAB)
+        r = np.asarray(rhoAB_vec, dtype=complex).reshape(dA, dA, dA, dA)
+        return np.hstack([np.trace(r, axis1=1, axis2=3).flatten(), np.trace(r, axis1=0, axis2=2).flatten()])
+
+    @staticmethod
+    def proj(rhoA_rhoB_vec):
+        half = len(rhoA_rhoB_vec) // 2
+        dA = isqrt(half)
+        v = np.asarray(rhoA_rhoB_vec, dtype=complex)
+        return np.kron(v[:half].reshape(dA, dA), v[half:].reshape(dA, dA)).flatten()
+
+
+_KINDS = {'identity': (_lib.LIFT_IDENTITY, QExperiment), 'coupled': (_lib.LIFT_COUPLED, QCoupledExperiment),
+          'trunc32': (_lib.LIFT_TRUNC32, QExperiment32)}
+
+
+class EnsembleQExperiment:
+    """N perturbed plants: H0 [N, d, d], H1 [N, m, d, d] complex (host arrays or CUDA tensors)."""
+
+    def __init__(self, H0, H1, kind='identity'):
+        self.H0 = H0
+        self.H1 = H1
+        self.kind = kind
+        self.lift_mode, self._cls = _KINDS[kind]
+        self.lift = self._cls.lift
+        self.proj = self._cls.proj
+
+    def __len__(self):
+        return self.H0.shape[0]
+
+    @property
+    def d(self):
+        return self.H0.shape[-1]
+
+    @property
+    def dim_u(self):
+        return self.H1.shape[1]
+
+    def member(self, k):
+        """The k-th plant as a single QExperiment of the matching class."""
+        H0 = self.H0[k].cpu().numpy() if hasattr(self.H0, 'cpu') else self.H0[k]
+        H1 = self.H1[k].cpu().numpy() if hasattr(self.H1, 'cpu') else self.H1[k]
+        return self._cls(np.array(H0), [np.array(h) for h in H1])
+
+    def slice(self, lo, hi):
+        return EnsembleQExperiment(self.H0[lo:hi], self.H1[lo:hi], self.kind)
+
+    def simulate(self, x0, u_seg, dt, return_propagators=False):
+        """x0 [N, d*d], u_seg [N, n_seg, m] -> device tensor [N, n_seg, d*d]."""
+        return expm_segments(x0, self.H0, self.H1, u_seg, dt, shared=False, return_propagators=return_propagators)

@@ -93,14 +93,14 @@ def _pack(**kw):
     return kw
 
 
-def config_qubit(order=1):
+def config_qubit(order=1, discretize=None):
     """BASELINE config 1 (tests/test_mpc4quantum.py:607-670): ideal qubit |0> -> |1>, 1 % detuned plant."""
     clock = StepClock(dt=1, horizon=10, n_steps=20)
     sat = 2 * np.pi * 0.1
     du = 0.5 * sat
     wq = 2 * np.pi * 4
     nominal = RWA_Qubit(wq, wq, wq)
-    A_init = discretize_homogeneous([liouvillian(h) for h in nominal.H_list], clock.dt, order)
+    A_init = (discretize or discretize_homogeneous)([liouvillian(h) for h in nominal.H_list], clock.dt, order)
     plant = RWA_Qubit(wq * 0.99, wq, wq)
     Q = np.diag([1.0, 0, 0, 1.0])
     R = (1e-2 / sat ** 2) * np.eye(1)
@@ -114,14 +114,14 @@ def config_qubit(order=1):
                  warm_start=True, target=target, wq=wq, nominal=nominal)
 
 
-def config_transmon(order=1, horizon=16, n_steps=20):
+def config_transmon(order=1, horizon=16, n_steps=20, discretize=None):
     """BASELINE config 3 (tests/test_mpc4quantum.py:504-564): 3-level transmon, DRAG-like state transfer."""
     clock = StepClock(dt=0.25, horizon=horizon, n_steps=n_steps)
     sat = 2 * np.pi * 0.25
     du = 0.5 * sat
     anharm = -2 * np.pi * 0.1 * (1 / clock.dt)
     qubit = RWA_Transmon(alpha=anharm)
-    A_init = discretize_homogeneous([liouvillian(h) for h in qubit.H_list], clock.dt, order)
+    A_init = (discretize or discretize_homogeneous)([liouvillian(h) for h in qubit.H_list], clock.dt, order)
     Q = np.zeros((9, 9))
     Q[0, 0] = 1
     Q[4, 4] = 1
@@ -137,15 +137,16 @@ def config_transmon(order=1, horizon=16, n_steps=20):
                  warm_start=True, target=target, anharm=anharm, nominal=qubit)
 
 
-def config_crosstalk(crosstalk=0.0, wiring='consistent'):
+def config_crosstalk(crosstalk=0.0, wiring='consistent', n_steps=50, discretize=None):
     """BASELINE config 4 (tests/test_mpc4quantum.py:281-368): two qubits, stacked 8-dim model, 16-dim plant.
 
     The reference test wires the model and the plant inconsistently: the model's first
     control drives qubit 2 with sy and omits the 1/2.  ``wiring='consistent'`` (default) builds the model from
     the plant's own single-qubit generators (u0 -> sx/2 on qubit A, u1 -> sy/2 on qubit B);
-    ``wiring='reference'`` reproduces the test literally.
+    ``wiring='reference'`` reproduces the test literally.  ``discretize`` replaces the device discretisation
+    (used by the CPU oracle, which has no GPU).
     """
-    clock = StepClock(dt=0.5, horizon=20, n_steps=50)
+    clock = StepClock(dt=0.5, horizon=20, n_steps=n_steps)
     clock.measure_freq = 2
     sat = 2 * np.pi * 0.1
     du = 0.25
@@ -160,7 +161,7 @@ def config_crosstalk(crosstalk=0.0, wiring='consistent'):
         A_cts = [blk(L1[0], L2[0]), blk(Z4, L2[1]), blk(L1[1], Z4)]
     else:
         A_cts = [blk(Z4, Z4), blk(liouvillian(0.5 * SX), Z4), blk(Z4, liouvillian(0.5 * SY))]
-    A_dst = discretize_homogeneous(A_cts, clock.dt, 1)
+    A_dst = (discretize or discretize_homogeneous)(A_cts, clock.dt, 1)
     r1, r2 = rx(-1e-3), rx(1e-3)
     rho1_init = r1 @ proj(2, 0) @ r1.conj().T
     rho2_init = r2 @ proj(2, 0) @ r2.conj().T
@@ -174,7 +175,7 @@ def config_crosstalk(crosstalk=0.0, wiring='consistent'):
     return _pack(name='crosstalk', x0=x0, dim_u=2, order=1,
                  X_targ=np.tile(target_model[:, None], (1, S + H + 1)), U_targ=np.zeros((2, S + H)),
                  clock=clock, experiment=qubits.QE, model=_dmdc(A_dst, 8), Q=Q, R=R, Qf=Q, sat=sat, du=du,
-                 warm_start=False, target=target_plant, nominal=qubits)
+                 warm_start=False, target=target_plant, nominal=qubits, kind='coupled')
 
 
 def _dmdc(A_full, c):

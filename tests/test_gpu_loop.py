@@ -1,0 +1,145 @@
+"""GPU parity of the closed loop (mpc.py:128-304) against the reference loop run through oracle/refshim.py with the
+restated QP / plant leaves (fixtures tests/golden/loop_*.npz), plus size-independent properties at full size."""
+import numpy as np
+import pytest
+
+import mpc4quantum_b200 as m4q
+from mpc4quantum_b200 import systems
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+U_TOL = 1e-5        # north_star: QP controls within 1e-5 absolute
+F_TOL = 1e-6        # north_star: closed-loop final-state fidelity within 1e-6
+
+
+def _fid(cfg, x_final):
+    return float(np.real(np.vdot(cfg['target'], x_final)))
+
+
+CASES = {
+    'loop_qubit_o1': lambda: systems.config_qubit(1),
+    'loop_qubit_o2': lambda: systems.config_qubit(2),
+    'loop_transmon_o1': lambda: systems.config_transmon(1),
+    'loop_transmon_o2': lambda: systems.config_transmon(2),
+    'loop_transmon_o1_h50': lambda: systems.config_transmon(1, horizon=50, n_steps=6),
+    'loop_crosstalk': lambda: systems.config_crosstalk(0.05, n_steps=12),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_mpc_matches_reference_loop(name):
+    g = load_golden(name)
+    cfg = CASES[name]()
+    assert np.abs(cfg['model'].A - g['A_full']).max() < 1e-13          # device discretisation == reference
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), model, exit_code = m4q.mpc(*args, **kw)
+    assert exit_code == 0 == int(g['exit_code'])
+    assert xs.shape == g['xs'].shape and us.shape == g['us'].shape
+    assert np.abs(us - g['us']).max() < U_TOL, np.abs(us - g['us']).max()
+    assert np.abs(xs - g['xs']).max() < 10 * U_TOL
+    assert abs(_fid(cfg, xs[:, -1]) - float(g['fidelity'])) < F_TOL
+    assert len(cfg['clock'].ts_sim) == cfg['clock'].n_steps
+
+
+@pytest.mark.parametrize('name,maker,n_total', [('loop_qubit_o1', systems.ensemble_qubit, 4096),
+                                                ('loop_transmon_o1', systems.ensemble_transmon, 65536),
+                                                ('loop_crosstalk', systems.ensemble_crosstalk, 65536)])
+def test_ensemble_members_match_oracle(name, maker, n_total):
+    g = load_golden(name)
+    cfg = CASES[name]()
+    ens, _ = maker(n_total)
+    k = g['ens_us'].shape[0]
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 64), *args[7:], fid_target=cfg['target'], **kw)
+    assert (res.exit_code == 0).all() and (res.steps_done == cfg['clock'].n_steps).all()
+    assert np.abs(res.us[:k] - g['ens_us']).max() < U_TOL, np.abs(res.us[:k] - g['ens_us']).max()
+    assert np.abs(res.xs[:k] - g['ens_xs']).max() < 10 * U_TOL
+    assert np.abs(res.fidelity[:k] - g['ens_fidelity']).max() < F_TOL
+    assert np.array_equal(res.qp_count[:k], g['ens_qp_per_step'])
+    assert (res.counters[:, 3] == res.qp_count.sum(axis=1)).all()
+
+
+def test_qp_counts_match_reference():
+    """Per-step SQP iteration counts are part of the loop's semantics (line-search stop test, mpc.py:224)."""
+    for name in ('loop_qubit_o1', 'loop_transmon_o1', 'loop_crosstalk'):
+        g = load_golden(name)
+        cfg = CASES[name]()
+        ens = m4q.EnsembleQExperiment(cfg['experiment'].H0[None], np.stack(cfg['experiment'].H1_list)[None],
+                                      cfg.get('kind', 'identity'))
+        args, kw = systems.mpc_args(cfg)
+        kw.pop('progress_bar')
+        res = m4q.mpc_ensemble(args[0], *args[1:6], ens, *args[7:], **kw)
+        assert np.array_equal(res.qp_count[0], g['qp_per_step']), (name, res.qp_count[0], g['qp_per_step'])
+
+
+def test_host_stepped_equals_fused():
+    """A user-defined Experiment goes through the one-step-per-launch path; same numbers as the fused kernel."""
+    cfg = systems.config_transmon(1, n_steps=6)
+    args, kw = systems.mpc_args(cfg)
+    (xs_f, us_f), _, ec_f = m4q.mpc(*args, **kw)
+
+    inner = cfg['experiment']
+
+    class MyPlant(m4q.Experiment):
+        def f(self, t, x, u):
+            raise NotImplementedError
+
+        def simulate(self, x0, ts, us):
+            return inner.simulate(x0, ts, us)
+    args = list(args)
+    args[6] = MyPlant()
+    (xs_h, us_h), _, ec_h = m4q.mpc(*args, **kw)
+    assert ec_f == ec_h == 0
+    assert np.abs(us_h - us_f).max() < 1e-12 and np.abs(xs_h - xs_f).max() < 1e-12
+
+
+def test_exit_condition_callback_and_return_shapes():
+    """exit code 1 and the early-exit slicing of mpc.py:298-304."""
+    cfg = systems.config_qubit(1)
+    args, kw = systems.mpc_args(cfg)
+    seen = []
+
+    def stop(x_next, x, u):
+        seen.append(1)
+        return len(seen) == 5
+    (xs, us), _, ec = m4q.mpc(*args, exit_condition=stop, **kw)
+    assert ec == 1 and xs.shape == (4, 5) and us.shape == (1, 4)
+    g = load_golden('loop_qubit_o1')
+    assert np.abs(us - g['us'][:, :4]).max() < U_TOL
+
+
+def test_full_size_properties_qubit_ensemble():
+    """BASELINE config 2 at full size (4,096 plants): invariants that need no oracle."""
+    cfg = systems.config_qubit(1)
+    ens, params = systems.ensemble_qubit(4096)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens, *args[7:], fid_target=cfg['target'], **kw)
+    S = cfg['clock'].n_steps
+    assert (res.exit_code == 0).all() and (res.steps_done == S).all()
+    assert np.abs(res.us).max() <= cfg['sat'] + 1e-12                                  # optimize.py:43
+    assert np.abs(np.diff(res.us[:, :, 1:], axis=2)).max() <= cfg['du'] + 1e-9         # optimize.py:30 from step 2 on
+    rho = res.xs.transpose(0, 2, 1).reshape(4096, S + 1, 2, 2)
+    assert np.abs(np.einsum('nsii->ns', rho) - 1).max() < 1e-10                        # unitary plant keeps the trace
+    assert np.abs(rho - rho.conj().transpose(0, 1, 3, 2)).max() < 1e-10
+    purity = np.real(np.einsum('nsij,nsji->ns', rho, rho))
+    assert np.abs(purity - purity[:, :1]).max() < 1e-9
+    assert np.abs(res.fidelity - np.real(res.xs[:, 3, -1])).max() < 1e-14
+    # step 0 does not see the plant yet: identical for every member
+    assert np.abs(res.us[:, :, 0] - res.us[0, :, 0]).max() == 0
+    assert (res.qp_count[:, 0] == res.qp_count[0, 0]).all()
+    # running the same members again, in a different batch composition, reproduces them bit for bit
+    sub = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(1000, 1100), *args[7:], fid_target=cfg['target'], **kw)
+    assert np.array_equal(sub.us, res.us[1000:1100]) and np.array_equal(sub.xs, res.xs[1000:1100])
+    assert 0.5 < np.median(res.fidelity) <= 1.0 + 1e-9
+
+
+def test_histogram_of_fidelities():
+    import torch
+    from mpc4quantum_b200.ensemble import fidelity_histogram
+    f = torch.rand(100000, dtype=torch.float64, device='cuda')
+    h = fidelity_histogram(f, 0.0, 1.0, 256).cpu().numpy()
+    ref, _ = np.histogram(f.cpu().numpy(), bins=256, range=(0.0, 1.0))
+    assert h.sum() == 100000 and np.array_equal(h, ref)

@@ -1,0 +1,128 @@
+"""GPU parity of the individual kernels, through the reference-shaped Python API (which calls the C ABI), against
+vectors produced by the reference's own functions (tests/golden/unit.npz, qp.npz; see oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+import mpc4quantum_b200 as m4q
+from mpc4quantum_b200 import optimize, systems
+from mpc4quantum_b200.experiment import expm_segments
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('tag,orders', [('qubit', (1, 2, 3)), ('transmon', (1, 2, 3)), ('coupled', (1, 2))])
+def test_discretize_homogeneous(unit_golden, tag, orders):
+    """vectorize.py:8-49; the reference's own test_discretization pins order 1 (tests/test_mpc4quantum.py:182-188)."""
+    L = unit_golden['disc_%s_L' % tag]
+    dt = float(unit_golden['disc_%s_dt' % tag])
+    for o in orders:
+        out = m4q.discretize_homogeneous(list(L), dt, o)
+        ref = unit_golden['disc_%s_o%d' % (tag, o)]
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() < 1e-13 * max(1.0, np.abs(ref).max())
+    c = L.shape[-1]
+    o1 = m4q.discretize_homogeneous(list(L), dt, 1)
+    assert np.abs(o1 - np.hstack([np.eye(c) + dt * L[0]] + [dt * l for l in L[1:]])).max() < 1e-14
+
+
+@pytest.mark.parametrize('tag,m', [('qubit', 1), ('transmon', 2), ('transmon1', 2), ('coupled', 3)])
+def test_linearize(unit_golden, tag, m):
+    """linearize.py:61-70 at random (X, U): A_t, B_t, Delta_t."""
+    A_full = unit_golden['lin_%s_A_full' % tag]
+    c = A_full.shape[0]
+    order = int(unit_golden['lin_%s_order' % tag])
+    wm = m4q.WrapModel(A_full[:, :c], A_full[:, c:], m, order)
+    X, U = unit_golden['lin_%s_X' % tag], unit_golden['lin_%s_U' % tag]
+    H = U.shape[1]
+    A, B, D = wm.get_model_along_traj(X, U, np.arange(H))
+    for got, ref in ((np.array(A), unit_golden['lin_%s_A' % tag]), (np.array(B), unit_golden['lin_%s_B' % tag]),
+                     (np.array(D)[:, :, 0], unit_golden['lin_%s_D' % tag])):
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    # single-point entry points agree with the trajectory ones
+    assert np.abs(wm.df_dx(X[:, 3], U[:, 3], 0) - A[3]).max() < 1e-13
+    assert np.abs(wm.df_du(X[:, 3], U[:, 3], 0) - B[3]).max() < 1e-13
+    f = wm.f(X[:, 3], U[:, 3], 0)
+    assert np.abs(f[:, 0] - (A[3] @ X[:, 3])).max() < 1e-11 * max(1.0, np.abs(f).max())   # f == A_t x
+
+
+@pytest.mark.parametrize('tag', ['qubit', 'transmon', 'transmon_full', 'cross'])
+def test_line_search(unit_golden, tag):
+    """mpc.py:101-125 including the time-major / state-major pairing."""
+    Q_ls, R_ls = list(unit_golden['ls_%s_Q' % tag]), list(unit_golden['ls_%s_R' % tag])
+    X, U = unit_golden['ls_%s_X' % tag], unit_golden['ls_%s_U' % tag]
+    alpha, step, _, _ = m4q.iqp_line_search(Q_ls, R_ls, X[0], U[0], X[1], U[1], X[2], U[2])
+    assert abs(alpha - float(unit_golden['ls_%s_alpha' % tag])) < 1e-12
+    assert abs(step - float(unit_golden['ls_%s_step' % tag])) < 1e-10
+
+
+@pytest.mark.parametrize('tag,maker', [('qubit', systems.ensemble_qubit), ('transmon', systems.ensemble_transmon),
+                                       ('cross', systems.ensemble_crosstalk)])
+def test_expm_propagators(unit_golden, tag, maker):
+    """Plant propagators within 1e-10 of scipy.linalg.expm (north_star tolerance); conjugation and trace."""
+    ens, _ = maker(16)
+    u = unit_golden['expm_%s_u' % tag]
+    ref = unit_golden['expm_%s_props' % tag]
+    dt = float(unit_golden['expm_%s_dt' % tag])
+    d = ens.d
+    rng = np.random.default_rng(3)
+    psi = rng.normal(size=(16, d)) + 1j * rng.normal(size=(16, d))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho0 = np.einsum('ni,nj->nij', psi, psi.conj()).reshape(16, d * d)
+    states, props = expm_segments(rho0, ens.H0, ens.H1, u, dt, return_propagators=True)
+    states, props = states.cpu().numpy(), props.cpu().numpy()
+    assert np.abs(props - ref).max() < 1e-10
+    assert np.abs(props - ref).max() < 5e-14       # what the kernel actually achieves
+    rho = rho0.reshape(16, d, d)
+    for sgm in range(3):
+        rho = ref[:, sgm] @ rho @ ref[:, sgm].conj().transpose(0, 2, 1)
+        assert np.abs(states[:, sgm] - rho.reshape(16, -1)).max() < 1e-12
+    assert np.abs(np.einsum('nii->n', states[:, -1].reshape(16, d, d)) - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize('tag', ['qubit', 'transmon', 'cross'])
+@pytest.mark.parametrize('polish', [1, 0])
+def test_quad_program(qp_golden, tag, polish):
+    """optimize.py:12-60 against the exact oracle solutions: controls within 1e-5 (north_star) in OSQP-equivalent
+    mode, and to 1e-8 in tight (polished) mode."""
+    g = qp_golden
+    n = g['%s_x_init' % tag].shape[0]
+    H = g['%s_U' % tag].shape[2]
+    Q_ls = [g['%s_Q' % tag]] * H + [g['%s_Qf' % tag]]
+    R_ls = [g['%s_R' % tag]] * H
+    settings = m4q._lib.qp_settings(polish=polish, max_admm=20000 if not polish else 0, eps=1e-7 if not polish else 0)
+    for i in range(n):
+        X, U, obj, info = optimize.quad_program(
+            g['%s_x_init' % tag][i], g['%s_X_bm' % tag][i], g['%s_U_bm' % tag][i], Q_ls, R_ls,
+            list(g['%s_A' % tag][i]), list(g['%s_B' % tag][i]), list(g['%s_D' % tag][i]), g['%s_u_prev' % tag][i],
+            float(g['%s_sat' % tag]), float(g['%s_du' % tag]), settings=settings)
+        assert info.status_code == 0
+        tol_u = 1e-8 if polish else 1e-5
+        assert np.abs(U - g['%s_U' % tag][i]).max() < tol_u, (tag, i, np.abs(U - g['%s_U' % tag][i]).max())
+        assert np.abs(X - g['%s_X' % tag][i]).max() < 100 * tol_u
+        assert abs(obj - float(g['%s_obj' % tag][i])) < 1e-6 * max(1.0, abs(float(g['%s_obj' % tag][i])))
+        sat, du = float(g['%s_sat' % tag]), float(g['%s_du' % tag])
+        assert np.abs(U).max() <= sat + 1e-12
+        assert np.abs(U[:, 0] - g['%s_u_prev' % tag][i]).max() <= du + 1e-12
+
+
+def test_quad_program_batched_matches_single(qp_golden):
+    g = qp_golden
+    tag = 'transmon'
+    n, H = g['%s_x_init' % tag].shape[0], g['%s_U' % tag].shape[2]
+    Q = np.broadcast_to(np.stack([g['%s_Q' % tag]] * H + [g['%s_Qf' % tag]]), (n, H + 1, 9, 9))
+    R = np.broadcast_to(np.stack([g['%s_R' % tag]] * H), (n, H, 2, 2))
+    X, U, obj, status, iters = optimize.quad_program_batched(
+        g['%s_x_init' % tag], g['%s_X_bm' % tag], g['%s_U_bm' % tag], Q, R, g['%s_A' % tag], g['%s_B' % tag],
+        g['%s_D' % tag], g['%s_u_prev' % tag], float(g['%s_sat' % tag]), float(g['%s_du' % tag]))
+    assert (status.cpu().numpy() == 0).all()
+    assert np.abs(U.cpu().numpy() - g['%s_U' % tag]).max() < 1e-8
+    assert (iters.cpu().numpy()[:, 1] >= 2).all()
+
+
+def test_sat_is_mandatory(qp_golden):
+    """optimize.py:43 fails without sat; so do we, loudly."""
+    g = qp_golden
+    with pytest.raises(TypeError):
+        optimize.quad_program(g['qubit_x_init'][0], g['qubit_X_bm'][0], g['qubit_U_bm'][0], [g['qubit_Q']] * 11,
+                              [g['qubit_R']] * 10, list(g['qubit_A'][0]), list(g['qubit_B'][0]), list(g['qubit_D'][0]))
