@@ -15,7 +15,7 @@ from scipy.linalg import expm
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from oracle import refshim, restate as rs          # noqa: E402
+from oracle import refshim, restate as rs, admm_model as am   # noqa: E402
 from mpc4quantum_b200 import systems               # noqa: E402  (pure-numpy system definitions only)
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -81,7 +81,7 @@ def reference_loop(cfg, plant=None):
     return data[0], data[1], exit_code, np.array(counts[:cfg['clock'].n_steps])
 
 
-def restated_loop(cfg, plant=None):
+def restated_loop(cfg, plant=None, qp=rs.qp_exact):
     src = plant if plant is not None else cfg['experiment']
     lift, proj = {'coupled': (rs.lift_coupled, rs.proj_coupled), 'trunc32': (rs.lift_32, None)}.get(
         cfg.get('kind'), (rs.lift_identity, rs.lift_identity))
@@ -90,7 +90,7 @@ def restated_loop(cfg, plant=None):
     xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
                              cfg['clock'].horizon, cfg['clock'].n_steps, pl, cfg['model'].A, cfg['Q'], cfg['R'],
                              cfg['Qf'], cfg['sat'], cfg['du'], warm_start=cfg['warm_start'],
-                             measure_freq=cfg['clock'].measure_freq, stats=stats)
+                             measure_freq=cfg['clock'].measure_freq, stats=stats, qp=qp)
     return xs, us, ec, np.array(stats['qp_per_step'])
 
 
@@ -111,11 +111,21 @@ def closed_loop_fixture(name, cfg, ensemble=None, n_members=0):
                restatement_gap=gap)
     if ensemble is not None and n_members:
         exps, params = ensemble
-        e_xs, e_us, e_fid, e_cnt = [], [], [], []
+        e_xs, e_us, e_fid, e_cnt, s_us, s_fid = [], [], [], [], [], []
         for k in range(n_members):
             member = exps.member(k)
             x, u, e, cnt = restated_loop(cfg, plant=member)
             assert e == 0
+            # conditioning of this member's closed loop: the same loop with a second exact QP solver (the numpy model
+            # of the device algorithm; single QPs agree with qp_exact to ~1e-14).  Badly mismatched plants amplify that
+            # round-off by up to 1e9 over the trajectory, which bounds how well ANY implementation can match.
+            warm = {}
+
+            def qp2(*a, **kw):
+                return am.qp_admm(*a, rho=0.1, eps=1e-2, warm=warm.get('warm'), stats=warm, **kw)
+            x2, u2, e2, cnt2 = restated_loop(cfg, plant=member, qp=qp2)
+            s_us.append(np.abs(u2 - u).max())
+            s_fid.append(abs(float(np.real(np.vdot(cfg['target'], x2[:, -1] - x[:, -1])))))
             if k == 0:      # anchor the ensemble path on the reference loop as well
                 xr, ur, er, cr = reference_loop(cfg, plant=member)
                 assert np.abs(xr - x).max() < 1e-6 and np.abs(ur - u).max() < 1e-6 and np.array_equal(cr, cnt)
@@ -124,8 +134,11 @@ def closed_loop_fixture(name, cfg, ensemble=None, n_members=0):
             e_cnt.append(cnt)
             e_fid.append(float(np.real(np.vdot(cfg['target'], x[:, -1]))))
         print('   ensemble members 0..%d: fidelity %s' % (n_members - 1, np.round(e_fid, 6)))
+        print('   closed-loop conditioning (second exact solver): |du| %s |dfid| %s'
+              % (np.array2string(np.array(s_us), precision=1), np.array2string(np.array(s_fid), precision=1)))
         out.update(ens_xs=np.array(e_xs), ens_us=np.array(e_us), ens_fidelity=np.array(e_fid),
-                   ens_qp_per_step=np.array(e_cnt))
+                   ens_qp_per_step=np.array(e_cnt), ens_us_sensitivity=np.array(s_us),
+                   ens_fid_sensitivity=np.array(s_fid))
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
 
 
