@@ -1,0 +1,145 @@
+"""CPU tests of the host layer: C-ABI surface, reference-shaped helpers, loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mpc4quantum_b200 as m4q
+from mpc4quantum_b200 import _lib, linearize, systems, vectorize
+from mpc4quantum_b200.ensemble import shard_bounds
+from oracle import restate as rs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'm4q.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(m4q_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(handle, name), name
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes table covers exactly the header
+    assert _lib.lib().m4q_version() == 100
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.QPSettings) == 40
+    assert ctypes.sizeof(_lib.MpcProblem) == 12 * 4 + 4 * 8 + 8 * 8 + 40
+    assert _lib.MpcProblem.dt.offset == 48 and _lib.MpcProblem.A_blocks.offset == 80
+
+
+def test_supported_instantiations_and_argument_errors():
+    lib = _lib.lib()
+    assert lib.m4q_supported(9, 2) and lib.m4q_supported(4, 1) and lib.m4q_supported(8, 2) and lib.m4q_supported(16, 3)
+    assert not lib.m4q_supported(5, 1)
+    prob = _lib.MpcProblem(c=5, m=1, p=1, d=2, horizon=4, n_steps=2, measure_freq=1, n_targ=7, sat=1.0)
+    assert lib.m4q_mpc_table_bytes(ctypes.byref(prob)) == -1
+    assert b'unsupported' in lib.m4q_last_error()
+    prob = _lib.MpcProblem(c=9, m=2, p=2, d=3, horizon=16, n_steps=20, measure_freq=1, n_targ=37, sat=0.0)
+    assert lib.m4q_mpc_state_bytes(ctypes.byref(prob), 4) == -1 and b'sat is mandatory' in lib.m4q_last_error()
+
+
+def test_launch_geometry_without_a_device():
+    lib = _lib.lib()
+    prob = _lib.MpcProblem(c=9, m=2, p=2, d=3, horizon=16, n_steps=20, measure_freq=1, n_targ=37, sat=1.0)
+    w, c, s = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert 1 <= w.value <= 16 and c.value % 148 == 0 and s.value <= 227 * 1024
+    prob.horizon = 400          # does not fit the shared-memory slab: refused, not truncated
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('this box has a GPU')
+    cfg = systems.config_qubit(1, discretize=rs.taylor_discretize)
+    args, kw = systems.mpc_args(cfg)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m4q.mpc(*args, **kw)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m4q.discretize_homogeneous([np.eye(4), np.eye(4)], 1.0, 1)
+
+
+def test_monomial_tables_match_reference_order():
+    assert [list(p) for p in linearize.create_power_list(2, 2)] == rs.power_table(2, 2).tolist()
+    assert [list(p) for p in linearize.create_power_list(3, 3)] == rs.power_table(3, 3).tolist()
+    assert linearize.size_of_library(2, 2) == 6 and linearize.size_of_library(1, 3) == 4
+    u = np.array([[0.5], [-2.0]])
+    lib_vals = [f(u)[0] for f in linearize.create_library(2, 2)]
+    assert np.allclose(lib_vals, [1, 0.5, 0.25, -2.0, -1.0, 4.0])
+    fns, coefs = linearize.diff_library(2, 2)
+    d0 = [c[0] * f(u)[0] for f, c in zip(fns[0], coefs[0])]          # d/du1 of u1, u1^2, u2, u1 u2, u2^2
+    assert np.allclose(d0, [1, 1.0, 0, -2.0, 0])
+
+
+def test_krtimes_and_wrapmodel_errors():
+    A = np.arange(6.0).reshape(2, 3)
+    B = np.arange(12.0).reshape(4, 3)
+    K = linearize.krtimes(A, B)
+    assert K.shape == (8, 3) and np.allclose(K[:, 1], np.kron(A[:, 1], B[:, 1]))
+    with pytest.raises(ValueError):
+        linearize.krtimes(A, B[:, :2])
+    with pytest.raises(ValueError, match='Dimension mismatch'):
+        linearize.WrapModel(np.eye(4), np.zeros((4, 12)), 1, 1)          # linearize.py:23-24
+
+
+def test_vectorize_me_is_the_liouvillian(unit_golden):
+    d = 3
+    H = systems.RWA_Transmon(-1.3).H_list[1]
+    basis = [np.outer(np.eye(d)[a], np.eye(d)[b]) for a in range(d) for b in range(d)]
+    assert np.abs(vectorize.vectorize_me(H, basis) - vectorize.liouvillian(H)).max() < 1e-14
+    out = vectorize.vectorize_me(unit_golden['vecme_H'], list(unit_golden['vecme_basis']))
+    assert np.abs(out - unit_golden['vecme_out']).max() < 1e-13
+
+
+def test_stepclock_and_helpers():
+    clock = m4q.StepClock(0.25, 16, 20)
+    clock.measure_freq = 2
+    assert np.allclose(clock.ts, np.linspace(0, 5.0, 20, endpoint=False))
+    assert np.allclose(clock.ts_step(3), [0.5, 0.75, 1.0]) and np.allclose(clock.ts_horizon(2)[:2], [0.5, 0.75])
+    assert clock.to_string() == 'mf_2d0e00_dt_2d5em01_h_1d6e01_n_2d0e01'
+    assert m4q.val_to_str(1.0) == '1d0e00'
+    z = np.array([1 + 2j, 3 - 1j])
+    assert np.allclose(m4q.real_to_complex(m4q.complex_to_real(z)), z)
+    P = np.array([[1 + 1j, 2], [0, 3j]])
+    assert np.allclose(m4q.real_to_complex_op(m4q.complex_to_real_op(P)), P)
+    assert np.allclose(m4q.shift_guess(np.arange(6.0).reshape(2, 3)), [[1, 2, 2], [4, 5, 5]])
+    clock.set_endsim(5)
+    assert len(clock.ts_sim) == 5
+
+
+def test_dmdc_container_and_lifts(unit_golden):
+    A = np.arange(24.0).reshape(2, 12)
+    model = m4q.DMDc(2, 4, 8, A)
+    A_x, A_u = model.get_discrete()
+    assert A_x.shape == (2, 4) and A_u.shape == (2, 8)
+    assert np.allclose(model.predict(np.ones(4), np.ones(8)), A.sum(axis=1, keepdims=True))
+    assert np.abs(m4q.QCoupledExperiment.lift(unit_golden['lift_rho']) - unit_golden['lift_out']).max() < 1e-14
+    assert np.abs(m4q.QCoupledExperiment.proj(unit_golden['lift_out']) - unit_golden['proj_out']).max() < 1e-14
+    rho3 = np.diag([0.6, 0.3, 0.1]).astype(complex).reshape(-1)
+    assert np.allclose(m4q.QExperiment32.lift(rho3), np.diag([2 / 3, 1 / 3]).reshape(-1))
+    assert m4q.isqrt(16) == 4
+    with pytest.raises(NotImplementedError):
+        m4q.OnlineDMDc(2, 4, 8, A).fit_iteration(None, None, None)
+
+
+def test_ensemble_draws_are_reproducible_and_shardable():
+    e1, p1 = systems.ensemble_transmon(64)
+    e2, p2 = systems.ensemble_transmon(64)
+    assert np.array_equal(e1.H0, e2.H0) and e1.H1.shape == (64, 2, 3, 3)
+    assert np.allclose(e1.H0, e1.H0.conj().transpose(0, 2, 1))
+    bounds = [shard_bounds(65536 + 3, r, 8) for r in range(8)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 65539
+    assert all(bounds[i][1] == bounds[i + 1][0] for i in range(7))
+    assert max(b - a for a, b in bounds) - min(b - a for a, b in bounds) == 1
+    sl = e1.slice(*shard_bounds(64, 1, 4))
+    assert len(sl) == 16 and np.array_equal(sl.H0, e1.H0[16:32])

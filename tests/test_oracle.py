@@ -1,0 +1,134 @@
+"""CPU tests of the oracle (oracle/restate.py, oracle/admm_model.py) against the fixtures generated from the
+reference's own code (oracle/make_golden.py).  No GPU, no /root/reference needed."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as rs, admm_model as am, refshim
+from mpc4quantum_b200 import systems
+from conftest import load_golden
+
+
+def test_power_table_matches_reference_order():
+    # for dim_u = 2, order = 2 the reference orders u1, u1^2, u2, u1 u2, u2^2
+    assert rs.power_table(2, 2).tolist() == [[0, 0], [1, 0], [2, 0], [0, 1], [1, 1], [0, 2]]
+    assert rs.power_table(1, 3).tolist() == [[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]
+
+
+@pytest.mark.parametrize('tag,orders', [('qubit', (1, 2, 3)), ('transmon', (1, 2, 3)), ('coupled', (1, 2))])
+def test_taylor_discretize_vs_reference(unit_golden, tag, orders):
+    L = list(unit_golden['disc_%s_L' % tag])
+    dt = float(unit_golden['disc_%s_dt' % tag])
+    for o in orders:
+        assert np.abs(rs.taylor_discretize(L, dt, o) - unit_golden['disc_%s_o%d' % (tag, o)]).max() < 1e-13
+
+
+def test_reference_test_discretization_case():
+    """The reference's only live hot-path assertion (tests/test_mpc4quantum.py:182-188): order 1, dt = 1."""
+    rng = np.random.default_rng(0)
+    A, N1, N2 = (rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)) for _ in range(3))
+    out = rs.taylor_discretize([A, N1, N2], 1.0, 1)
+    assert np.allclose(out, np.hstack([np.eye(8) + A, N1, N2]))
+
+
+def test_vectorize_me_restatement(unit_golden):
+    out = rs.liouvillian_in_basis(unit_golden['vecme_H'], list(unit_golden['vecme_basis']))
+    assert np.abs(out - unit_golden['vecme_out']).max() < 1e-13
+
+
+@pytest.mark.parametrize('tag,m', [('qubit', 1), ('transmon', 2), ('transmon1', 2), ('coupled', 3)])
+def test_linearisation_vs_reference(unit_golden, tag, m):
+    bm = rs.BilinearModel(unit_golden['lin_%s_A_full' % tag], m, int(unit_golden['lin_%s_order' % tag]))
+    X, U = unit_golden['lin_%s_X' % tag], unit_golden['lin_%s_U' % tag]
+    A, B, D = bm.along(X, U, U.shape[1])
+    assert np.abs(np.array(A) - unit_golden['lin_%s_A' % tag]).max() < 1e-12
+    assert np.abs(np.array(B) - unit_golden['lin_%s_B' % tag]).max() < 1e-12
+    assert np.abs(np.array(D) - unit_golden['lin_%s_D' % tag]).max() < 1e-11
+    # Delta_t == -B_t u_t identically and the Jacobian agrees with central differences
+    assert np.abs(np.array(D) + np.einsum('tij,jt->ti', np.array(B), U)).max() < 1e-11
+    eps = 1e-6
+    e0 = np.zeros(m)
+    e0[0] = eps
+    fd = (bm.step(X[:, 2], U[:, 2] + e0) - bm.step(X[:, 2], U[:, 2] - e0)) / (2 * eps)
+    assert np.abs(fd - B[2][:, 0]).max() < 1e-7
+
+
+@pytest.mark.parametrize('tag', ['qubit', 'transmon', 'transmon_full', 'cross'])
+def test_line_search_quirk_vs_reference(unit_golden, tag):
+    X, U = unit_golden['ls_%s_X' % tag], unit_golden['ls_%s_U' % tag]
+    a, s = rs.line_search(list(unit_golden['ls_%s_Q' % tag]), list(unit_golden['ls_%s_R' % tag]), X[0], U[0], X[1], U[1],
+                          X[2], U[2])
+    assert abs(a - float(unit_golden['ls_%s_alpha' % tag])) < 1e-12
+    assert abs(s - float(unit_golden['ls_%s_step' % tag])) < 1e-10
+
+
+def test_partial_trace_and_kron(unit_golden):
+    """The reference's test_partialTrace (tests/test_mpc4quantum.py:190-213) restated: product states round-trip."""
+    assert np.abs(rs.lift_coupled(unit_golden['lift_rho']) - unit_golden['lift_out']).max() < 1e-14
+    assert np.abs(rs.proj_coupled(unit_golden['lift_out']) - unit_golden['proj_out']).max() < 1e-14
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    b = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    a, b = a @ a.conj().T, b @ b.conj().T
+    a, b = a / np.trace(a), b / np.trace(b)
+    stacked = rs.lift_coupled(np.kron(a, b).reshape(-1))
+    assert np.allclose(stacked, np.concatenate([a.reshape(-1), b.reshape(-1)]))
+    assert np.allclose(rs.proj_coupled(stacked), np.kron(a, b).reshape(-1))
+
+
+@pytest.mark.parametrize('tag', ['qubit', 'transmon', 'cross'])
+def test_qp_oracles_agree_and_are_kkt_certified(qp_golden, tag):
+    """Exact active-set oracle == stored solutions; the numpy model of the device ADMM+polish lands on the same
+    optimum; both carry a KKT certificate that does not depend on how the solution was found."""
+    g = qp_golden
+    H = g['%s_U' % tag].shape[2]
+    for i in (0, 2, 5):
+        args = (g['%s_x_init' % tag][i], g['%s_X_bm' % tag][i], g['%s_U_bm' % tag][i], [g['%s_Q' % tag]] * H + [g['%s_Qf' % tag]],
+                [g['%s_R' % tag]] * H, list(g['%s_A' % tag][i]), list(g['%s_B' % tag][i]), list(g['%s_D' % tag][i]),
+                g['%s_u_prev' % tag][i], float(g['%s_sat' % tag]), float(g['%s_du' % tag]))
+        X, U, obj, info = rs.qp_exact(*args)
+        assert np.abs(U - g['%s_U' % tag][i]).max() < 1e-10
+        assert info['kkt'][0] < 1e-8 and info['kkt'][1] < 1e-12
+        X2, U2, obj2, _ = am.qp_admm(*args, rho=0.1, eps=1e-2)
+        assert np.abs(U2 - U).max() < 1e-9 and abs(obj2 - obj) < 1e-9 * max(1, abs(obj))
+        kkt = rs.qp_kkt(info, U2)
+        assert kkt[0] < 1e-8 and kkt[1] < 1e-12
+        # a perturbed point is NOT certified: the certificate has teeth
+        assert rs.qp_kkt(info, np.clip(U + 1e-3, -args[9], args[9]))[0] > 1e-6
+
+
+def test_restated_loop_reproduces_reference_run():
+    """oracle/restate.mpc_loop == the reference's mpc() (run through the shim when the fixture was made)."""
+    g = load_golden('loop_qubit_o1')
+    cfg = systems.config_qubit(1, discretize=rs.taylor_discretize)
+    assert np.abs(cfg['model'].A - g['A_full']).max() < 1e-14
+    plant = rs.ExpmPlant(cfg['experiment'].H0, cfg['experiment'].H1_list)
+    stats = {}
+    xs, us, ec = rs.mpc_loop(cfg['x0'], 1, 1, cfg['X_targ'], cfg['U_targ'], 1.0, 10, 20, plant, cfg['model'].A, cfg['Q'],
+                             cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], stats=stats)
+    assert ec == 0 and stats['qp_per_step'] == list(g['qp_per_step'])
+    assert np.abs(us - g['us']).max() < 1e-6 and np.abs(xs - g['xs']).max() < 1e-6
+    assert abs(float(np.real(xs[3, -1])) - 0.999479038) < 1e-8          # SURVEY 8c smoke value
+    assert np.allclose(us[0, :3], [0.31416, 0.31416, 0.62832], atol=1e-5)
+
+
+def test_loop_quirks_are_exercised_by_fixture():
+    """measure_freq = 2, warm_start = False, lift/proj (crosstalk config): newest-first control window (mpc.py:257),
+    lagging targets, model steps between measurements -- all of it inside the stored reference run."""
+    g = load_golden('loop_crosstalk')
+    cfg = systems.config_crosstalk(0.05, n_steps=4, discretize=rs.taylor_discretize)
+    plant = rs.ExpmPlant(cfg['experiment'].H0, cfg['experiment'].H1_list, rs.lift_coupled, rs.proj_coupled)
+    xs, us, ec = rs.mpc_loop(cfg['x0'], 2, 1, cfg['X_targ'], cfg['U_targ'], 0.5, 20, 4, plant, cfg['model'].A, cfg['Q'],
+                             cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], warm_start=False, measure_freq=2)
+    assert ec == 0
+    assert np.abs(us - g['us'][:, :4]).max() < 1e-7 and np.abs(xs - g['xs'][:, :5]).max() < 1e-7
+    # odd steps are model predictions pushed through proj: product states
+    x1 = xs[:, 1]
+    assert np.abs(rs.proj_coupled(rs.lift_coupled(x1)) - x1).max() < 1e-12
+
+
+@pytest.mark.skipif(not refshim.available(), reason='reference tree only exists in the build container')
+def test_shim_runs_reference_functions():
+    lin = refshim.module('linearize')
+    assert [list(p) for p in lin.create_power_list(2, 2)] == rs.power_table(2, 2).tolist()
