@@ -175,6 +175,8 @@ def main():
     ap.add_argument('--members', type=int, default=65536, help='ensemble members per GPU (weak scaling)')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--admm-first', action='store_true',
+                    help='always run an ADMM block before the active-set rounds (m4q_qp_settings.admm_first)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -202,7 +204,8 @@ def main():
     margs = (cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'], cfg['model'], cfg['Q'], cfg['R'],
              cfg['Qf'], cfg['sat'], cfg['du'])
     plan = m4q.ClosedLoopPlan(*margs, d=ens.d, lift_mode=ens.lift_mode, warm_start=cfg['warm_start'],
-                              fid_target=cfg['target'], capacity=n)
+                              fid_target=cfg['target'], capacity=n,
+                              settings=_lib.qp_settings(admm_first=int(args.admm_first)))
     geom = plan.launch_info()
 
     # ---- resident inputs (value) and pinned host inputs (e2e)
@@ -301,6 +304,15 @@ def main():
         torch.cuda.synchronize()
         best = max(best, 2.0 * 16 * iters * 256 * ctas / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     fp64_peak = best
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().m4q_fp64_dmma_probe(ctas, iters >> 2, _lib.ptr(scratch), _lib.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 512.0 * 8 * (iters >> 2) * 8 * ctas / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    dmma_peak = best
 
     e2e_ms, _ = timed(e2e_pass, max(2, min(args.steps, 3)))
     e2e_steps = max(2, min(args.steps, 3))
@@ -325,8 +337,10 @@ def main():
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': '%s: 3-level transmon (c=%d, m=%d), horizon %d, %d MPC steps, %d perturbed plants per GPU '
-                               '(seed 20220113), tight QP mode' % (args.workload, cfg['model'].A.shape[0], cfg['dim_u'],
-                                                                   cfg['clock'].horizon, S, args.members),
+                               '(seed 20220113), tight QP mode (%s)' % (args.workload, cfg['model'].A.shape[0], cfg['dim_u'],
+                                                                   cfg['clock'].horizon, S, args.members,
+                                                                   'ADMM block first' if args.admm_first else
+                                                                   'warm active set first, ADMM fallback'),
                    'members_total': n_total, 'l2': 'flushed between timed passes (256 MB write, untimed)',
                    'launch': geom},
         'qp_solves_per_s': qp_total_all * args.steps / (total_ms * 1e-3),
@@ -341,6 +355,7 @@ def main():
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                      'frac': achieved / fp64_peak, 'traffic': None,
                      'peak_source': 'm4q_fp64_fma_probe measured in this run (MEASURED_PEAKS.json has no fp64 figure)',
+                     'dmma_probe_tflops': dmma_peak,
                      'kernel': 'mpc_kernel', 'kernel_ms': kernel_ms, 'flops_per_launch': flops,
                      'flops_per_trajectory': flops / n, 'flop_model': per_unit,
                      'hbm': {'algorithmic_bytes': int(hbm_alg), 'achieved_gbs': hbm_alg / (kernel_ms * 1e-3) / 1e9}},

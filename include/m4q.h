@@ -40,7 +40,8 @@ typedef struct {
     int32_t max_admm;    /* ADMM iterations per block                    (default 400)  */
     int32_t polish;      /* 1: active-set polish + KKT certificate (tight mode); 0: OSQP-equivalent mode */
     int32_t max_polish;  /* active-set rounds per polish                 (default 8)    */
-    int32_t reserved;
+    int32_t admm_first;  /* tight mode only. 0: warm-started active-set rounds first, ADMM block as fallback (default);
+                            1: always run an ADMM block to eps before the active-set rounds */
 } m4q_qp_settings;
 
 /* Problem description of the closed loop (mpc.py:128-304).  Shared (member-independent) data. */
@@ -183,6 +184,8 @@ int m4q_hist_fidelity(int64_t N, const double *fidelity, double lo, double hi, i
  * denominator on the part the benchmark runs on.  scratch: >= 8 bytes of device memory.
  */
 int m4q_fp64_fma_probe(int32_t ctas, int64_t iters, double *scratch, void *stream);
+/* same for the fp64 tensor-core path: each warp issues 8 * iters mma.sync.m8n8k4.f64 (512 flops each) */
+int m4q_fp64_dmma_probe(int32_t ctas, int64_t iters, double *scratch, void *stream);
 
 #ifdef __cplusplus
 }

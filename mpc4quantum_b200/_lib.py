@@ -19,7 +19,7 @@ c_i32, c_i64, c_f64, c_vp = ct.c_int32, ct.c_int64, ct.c_double, ct.c_void_p
 class QPSettings(ct.Structure):
     """m4q_qp_settings (include/m4q.h)."""
     _fields_ = [('rho', c_f64), ('alpha', c_f64), ('eps', c_f64), ('max_admm', c_i32), ('polish', c_i32),
-                ('max_polish', c_i32), ('reserved', c_i32)]
+                ('max_polish', c_i32), ('admm_first', c_i32)]
 
 
 class MpcProblem(ct.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
                                        ct.POINTER(c_i32)]),
     'm4q_hist_fidelity': (ct.c_int, [c_i64, c_vp, c_f64, c_f64, c_i32, c_vp, c_vp]),
     'm4q_fp64_fma_probe': (ct.c_int, [c_i32, c_i64, c_vp, c_vp]),
+    'm4q_fp64_dmma_probe': (ct.c_int, [c_i32, c_i64, c_vp, c_vp]),
 }
 
 _lib = None
@@ -131,6 +132,6 @@ def stream_ptr(stream=None):
     return c_vp(st.cuda_stream)
 
 
-def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0):
+def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0, admm_first=0):
     """Zeros select the library defaults (include/m4q.h)."""
-    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, 0)
+    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, admm_first)

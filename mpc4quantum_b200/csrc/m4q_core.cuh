@@ -23,20 +23,27 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 // ---------------------------------------------------------------------------------------------------------
 // Compile-time configuration for a (complex state dim, control dim) pair.
-// TR1 x TC1: register tile of W = P^T [A|B] (N x Q);  TR2 x TC2: register tile of [A|B]^T W (Q x Q).
+// TR1 x TC1: register tile of W = P [A|B] (N x Q).  TS x TS: register tile of [A|B]^T W, of which only the
+// upper block triangle of the N x N part and the M control rows are computed (the product is symmetric).
 // ---------------------------------------------------------------------------------------------------------
-template <int C_, int M_> struct Tiles { static constexpr int TR1 = 2, TC1 = 4, TR2 = 4, TC2 = 4; };
-template <> struct Tiles<4, 1>  { static constexpr int TR1 = 2, TC1 = 3, TR2 = 3, TC2 = 3; };
-template <> struct Tiles<9, 2>  { static constexpr int TR1 = 3, TC1 = 4, TR2 = 4, TC2 = 4; };
-template <> struct Tiles<8, 2>  { static constexpr int TR1 = 2, TC1 = 5, TR2 = 4, TC2 = 4; };
-template <> struct Tiles<16, 3> { static constexpr int TR1 = 4, TC1 = 9, TR2 = 6, TC2 = 9; };
+// MAXW: most warps (members) a CTA is ever launched with; it fixes the register budget (__launch_bounds__).
+template <int C_, int M_> struct Tiles { static constexpr int TR1 = 2, TC1 = 4, TS = 2, MAXW = 16; };
+template <> struct Tiles<4, 1>  { static constexpr int TR1 = 2, TC1 = 3, TS = 2, MAXW = 16; };
+template <> struct Tiles<9, 2>  { static constexpr int TR1 = 3, TC1 = 4, TS = 3, MAXW = 8; };
+template <> struct Tiles<8, 2>  { static constexpr int TR1 = 2, TC1 = 5, TS = 4, MAXW = 8; };
+template <> struct Tiles<16, 3> { static constexpr int TR1 = 4, TC1 = 9, TS = 4, MAXW = 4; };
 
 template <int C_, int M_> struct Cfg {
     static constexpr int C = C_, N = 2 * C_, M = M_, Q = N + M_;
     using T = Tiles<C_, M_>;
-    static constexpr int TR1 = T::TR1, TC1 = T::TC1, TR2 = T::TR2, TC2 = T::TC2;
-    static_assert(N % TR1 == 0, "row tile of mm1 must divide N");
-    static constexpr int LD = rup(cmax(cmax(rup(Q, TC1), rup(Q, TR2)), rup(Q, TC2)), 2);
+    static constexpr int TR1 = T::TR1, TC1 = T::TC1, TS = T::TS, MAXW = T::MAXW;
+    static_assert(N % TR1 == 0, "row tile of W must divide N");
+    static_assert(N % TS == 0, "tile of the symmetric product must divide N");
+    static_assert(TS >= M, "control rows must fit in one tile row");
+    // tiles of the symmetric product: upper block triangle of T11 plus one row of tiles for [T21 | T22]
+    static constexpr int NT = N / TS, NT11 = NT * (NT + 1) / 2, NT2 = cdiv(Q, TS), NTILES = NT11 + NT2;
+    static constexpr int ROUNDS = cdiv(NTILES, 32);
+    static constexpr int LD = rup(cmax(cmax(rup(Q, TC1), N + TS), rup(Q, TS)), 2);
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -98,6 +105,24 @@ template <class CF> struct Slab {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// The large device functions below are __noinline__ (one copy each: the hot code has to stay resident in the
+// instruction cache) and therefore re-derive every shared-memory pointer from the dynamic shared-memory base, so
+// that the compiler keeps emitting LDS/STS instead of generic loads.  A slab is named by its offset (in doubles).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double *dyn_smem() {
+    extern __shared__ double2 m4q_dyn_smem[];
+    return reinterpret_cast<double *>(m4q_dyn_smem);
+}
+struct SlabRef {
+    int off, H, nblk, dd;
+};
+template <class CF> __device__ __forceinline__ Slab<CF> slab_view(const SlabRef &r) {
+    Slab<CF> s;
+    Slab<CF>::layout(&s, dyn_smem() + r.off, r.H, r.nblk, r.dd);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Stage operator A_t = sum_k w_k(t) block_k.  Fused loop: blocks = shared model [A, N_1..N_p], w = monomials of
 // the guess control (held in slab.phi).  Stand-alone QP: one dense block per stage, w = 1.
 // ---------------------------------------------------------------------------------------------------------
@@ -105,7 +130,14 @@ struct StageOps {
     const double2 *blocks;   // [nblk][C][C] (fused: shared memory) or [H][C][C] (dense: global memory)
     int nblk;
     int stage_stride;        // in complex elements; 0 for the fused model
+    int soff;                // FUSED: offset (doubles) of the blocks in dynamic shared memory
 };
+// FUSED = true: model blocks and cost matrices live in dynamic shared memory at known offsets
+template <bool FUSED> __device__ __forceinline__ StageOps localize(const StageOps &o) {
+    StageOps r = o;
+    if (FUSED) r.blocks = reinterpret_cast<const double2 *>(dyn_smem() + o.soff);
+    return r;
+}
 
 // Data of one QP instance that is not in the slab (targets and costs, pre-realified by a prep kernel).
 struct QPData {
@@ -121,11 +153,21 @@ struct QPData {
     const double *Rub;    // R(t) ub(t)
     double sat;
     int q_diag;           // 1 if every Qbar is diagonal (fast path of the line search / adjoint)
+    int Q_soff, Qf_soff, R_soff;   // FUSED: offsets (doubles) of Q, Qf, R in dynamic shared memory
 };
+template <bool FUSED> __device__ __forceinline__ QPData localize(const QPData &q) {
+    QPData r = q;
+    if (FUSED) {
+        r.Q = dyn_smem() + q.Q_soff;
+        r.Qf = dyn_smem() + q.Qf_soff;
+        r.R = dyn_smem() + q.R_soff;
+    }
+    return r;
+}
 
 struct QPSet {
     double rho, alpha, eps;
-    int max_admm, polish, max_polish;
+    int max_admm, polish, max_polish, admm_first;
 };
 
 struct Counters {
@@ -142,6 +184,24 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
+// Sum M values over the warp, result in every lane.  Two values share one butterfly: the first exchange sends the
+// value a lane does not keep, so 6 shuffle stages replace 10.
+template <int M> __device__ __forceinline__ void warp_sum_vec(double (&g)[M], int lane) {
+    if constexpr (M >= 2) {
+        const bool hi = (lane & 16) != 0;
+        double keep = hi ? g[1] : g[0];
+        keep += __shfl_xor_sync(FULL, hi ? g[0] : g[1], 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(FULL, keep, o);
+        const double other = __shfl_xor_sync(FULL, keep, 16);
+        g[0] = hi ? other : keep;
+        g[1] = hi ? keep : other;
+#pragma unroll
+        for (int i = 2; i < M; ++i) g[i] = warp_sum(g[i]);
+    } else {
+        g[0] = warp_sum(g[0]);
+    }
+}
 
 // out[i][j] = sum_k X[k][i] * Y[k][j], register tile TR x TC per lane, tiles round-robin over lanes.
 template <int TR, int TC, int NK, int NI, int NJ, class Sink>
@@ -156,7 +216,7 @@ __device__ __forceinline__ void xty(const double *__restrict__ X, int ldx, const
 #pragma unroll
             for (int b = 0; b < TC; ++b) acc[a][b] = 0.0;
         const double *xp = X + i0, *yp = Y + j0;
-#pragma unroll 2
+#pragma unroll(NK % 3 == 0 ? 3 : 2)
         for (int k = 0; k < NK; ++k) {
             double xv[TR], yv[TC];
 #pragma unroll
@@ -203,52 +263,54 @@ template <int M> __device__ __forceinline__ void spd_inverse(double (&a)[M][M], 
     }
 }
 
-// y[k] = (A_t x)[k] for lane k < N, x realified in shared memory.  Branch-free over the re/im halves.
-template <class CF>
-__device__ __forceinline__ double apply_A(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
+// ---------------------------------------------------------------------------------------------------------
+// y[lane] = (A_t x)[lane] (TRANS = false) or (A_t^T x)[lane] (TRANS = true) for lane < N; x realified
+// [Re | Im] in shared memory.  A_t = sum_k phi_k blk_k is never formed: with m = blk_k[r][j] (or [j][r]),
+//   A,   re row:  sum m.x xr - m.y xi      A,   im row:  sum m.x xi + m.y xr
+//   A^T, re row:  sum m.x xr + m.y xi      A^T, im row:  sum m.x xi - m.y xr
+// so each lane reads x through two lane-dependent base pointers and one sign: no selects in the loop.
+// The vector is cached in registers across the blocks; four accumulator chains per block.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF, bool TRANS>
+__device__ __forceinline__ double cmatvec(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
     constexpr int C = CF::C, N = CF::N;
     if (lane >= N) return 0.0;
-    const int r = lane % C;
     const bool im = lane >= C;
-    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + r * C;
+    const int r = im ? lane - C : lane;
+    const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
+    const double sgn = (im != TRANS) ? 1.0 : -1.0;
+    double pv[C], qv[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        pv[j] = xp[j];
+        qv[j] = xq[j];
+    }
+    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + (TRANS ? r : r * C);
     double out = 0.0;
     for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
-        double s0 = 0.0, s1 = 0.0;
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            const double2 mij = blk[j];
-            const double a = im ? mij.y : mij.x;
-            const double b = im ? mij.x : -mij.y;
-            s0 = fma(a, x[j], s0);
-            s1 = fma(b, x[C + j], s1);
+            const double2 m = blk[TRANS ? j * C : j];
+            if (j & 1) {
+                p1 = fma(m.x, pv[j], p1);
+                q1 = fma(m.y, qv[j], q1);
+            } else {
+                p0 = fma(m.x, pv[j], p0);
+                q0 = fma(m.y, qv[j], q0);
+            }
         }
-        out = fma(phi_t[kb], s0 + s1, out);
+        out = fma(phi_t[kb], fma(sgn, q0 + q1, p0 + p1), out);
     }
     return out;
 }
-
-// y[k] = (A_t^T v)[k] for lane k < N
+template <class CF>
+__device__ __forceinline__ double apply_A(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
+    return cmatvec<CF, false>(ops, phi_t, t, x, lane);
+}
 template <class CF>
 __device__ __forceinline__ double apply_AT(const StageOps &ops, const double *phi_t, int t, const double *v, int lane) {
-    constexpr int C = CF::C, N = CF::N;
-    if (lane >= N) return 0.0;
-    const int r = lane % C;
-    const bool im = lane >= C;
-    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + r;
-    double out = 0.0;
-    for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const double2 mjr = blk[j * C];
-            const double a = im ? -mjr.y : mjr.x;
-            const double b = im ? mjr.x : mjr.y;
-            s0 = fma(a, v[j], s0);
-            s1 = fma(b, v[C + j], s1);
-        }
-        out = fma(phi_t[kb], s0 + s1, out);
-    }
-    return out;
+    return cmatvec<CF, true>(ops, phi_t, t, v, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -264,17 +326,48 @@ template <class CF> __device__ __forceinline__ double box_hi(const Slab<CF> &s, 
 // ---------------------------------------------------------------------------------------------------------
 // Riccati matrix sweep.  masked: controls with mask != 0 are pinned to their bound (polish), rho_half = 0.
 // Produces K_t, S_t^-1, dv_t = P_{t+1} (D_t + B_fixed b) for all stages.
+//
+// Per stage, with G = [A_t | B~_t] (N x Q):  W = P G  (3x4 register tiles), then T = G^T W, which is symmetric:
+// only the upper block triangle of T11 = A^T P A and the M control rows [T21 | T22] are computed, one TS x TS
+// tile per lane, accumulators kept in registers across the warp sync that publishes T21 / T22, and the update
+//   P_t = Qbar_t + T11 - T21^T S^-1 T21,   S = R + rho/2 + T22
+// is applied in the tile epilogue and mirrored, so P stays exactly symmetric and T11 never touches memory.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF>
-__device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, double rho_half,
-                               bool masked, int lane) {
-    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q, LD = CF::LD;
-    for (int e = lane; e < N * N; e += 32) s.P[e] = qp.Qf[e];
-    if constexpr (LD > Q) {   // zero the padding columns once
-        for (int e = lane; e < N * (LD - Q); e += 32) {
-            const int k = e / (LD - Q), j = Q + e % (LD - Q);
-            s.AB[k * LD + j] = 0.0;
+template <class CF, bool FUSED>
+__device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
+                                            bool masked, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q, LD = CF::LD, TS = CF::TS;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
+    constexpr int NT = CF::NT, NT11 = CF::NT11, NTILES = CF::NTILES, ROUNDS = CF::ROUNDS;
+    // tile coordinates of this lane (fixed for the whole sweep)
+    int ti0[ROUNDS], tj0[ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int tile = lane + 32 * rd;
+        if (tile < NT11) {   // unrank (bi <= bj)
+            int bi = 0, rem = tile;
+            while (rem >= NT - bi) {
+                rem -= NT - bi;
+                ++bi;
+            }
+            ti0[rd] = bi * TS;
+            tj0[rd] = (bi + rem) * TS;
+        } else if (tile < NTILES) {
+            ti0[rd] = N;
+            tj0[rd] = (tile - NT11) * TS;
+        } else {
+            ti0[rd] = -1;
+            tj0[rd] = 0;
         }
+    }
+    for (int e = lane; e < N * N; e += 32) s.P[e] = qp.Qf[e];
+    for (int e = lane; e < N * (LD - Q); e += 32) {   // zero the padding columns once
+        const int k = e / (LD - Q), j = Q + e % (LD - Q);
+        s.AB[k * LD + j] = 0.0;
+        s.W[k * LD + j] = 0.0;
     }
     __syncwarp();
     for (int t = H - 1; t >= 0; --t) {
@@ -325,15 +418,39 @@ __device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPD
         // W = P [A | B~]
         xty<CF::TR1, CF::TC1, N, N, Q>(s.P, N, s.AB, LD, lane, [&](int i, int j, double v) { s.W[i * LD + j] = v; });
         __syncwarp();
-        // [A | B~]^T W : T11 -> P, T21 -> T21, T22 -> S
-        xty<CF::TR2, CF::TC2, N, Q, Q>(s.AB, LD, s.W, LD, lane, [&](int i, int j, double v) {
-            if (j < N) {
-                if (i < N) s.P[i * N + j] = v;
-                else s.T21[(i - N) * N + j] = v;
-            } else if (i >= N) {
-                s.S[(i - N) * M + (j - N)] = v;
+        // T tiles: acc[a][b] = sum_k G[k][i0 + a] W[k][j0 + b]
+        double acc[ROUNDS][TS][TS];
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+#pragma unroll
+            for (int a = 0; a < TS; ++a)
+#pragma unroll
+                for (int b = 0; b < TS; ++b) acc[rd][a][b] = 0.0;
+            if (ti0[rd] < 0) continue;
+            const double *xp = s.AB + ti0[rd], *yp = s.W + tj0[rd];
+#pragma unroll(N % 3 == 0 ? 3 : 2)
+            for (int k = 0; k < N; ++k) {
+                double xv[TS], yv[TS];
+#pragma unroll
+                for (int a = 0; a < TS; ++a) xv[a] = xp[k * LD + a];
+#pragma unroll
+                for (int b = 0; b < TS; ++b) yv[b] = yp[k * LD + b];
+#pragma unroll
+                for (int a = 0; a < TS; ++a)
+#pragma unroll
+                    for (int b = 0; b < TS; ++b) acc[rd][a][b] = fma(xv[a], yv[b], acc[rd][a][b]);
             }
-        });
+            if (ti0[rd] == N) {   // control rows: publish T21 and T22
+#pragma unroll
+                for (int a = 0; a < M; ++a)
+#pragma unroll
+                    for (int b = 0; b < TS; ++b) {
+                        const int j = tj0[rd] + b;
+                        if (j < N) s.T21[a * N + j] = acc[rd][a][b];
+                        else if (j < Q) s.S[a * M + (j - N)] = acc[rd][a][b];
+                    }
+            }
+        }
         __syncwarp();
         // S = R~ + rho/2 + B~^T P B~ ; invert (every lane redundantly, M <= 3)
         double Sm[M][M], Si[M][M];
@@ -366,20 +483,34 @@ __device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPD
                 s.K[(t * M + a) * N + lane] = kv;
             }
         }
-        __syncwarp();
-        // P_t = Qbar_t + sym(T11) - T21^T K   (one lane per unordered pair keeps P exactly symmetric)
+        // P_t = Qbar_t + T11 - T21^T K on the upper block triangle, mirrored
         const double *Qt = qp.Q + t * qp.q_stride;
-        const double *Kt = s.K + t * M * N;
-        for (int e = lane; e < N * (N + 1) / 2; e += 32) {
-            // unrank e -> (i <= j)
-            int i = 0, rem = e;
-            while (rem >= N - i) { rem -= N - i; ++i; }
-            const int j = i + rem;
-            double v = 0.5 * (s.P[i * N + j] + s.P[j * N + i]) + Qt[i * N + j];
 #pragma unroll
-            for (int a = 0; a < M; ++a) v = fma(-s.T21[a * N + i], Kt[a * N + j], v);
-            s.P[i * N + j] = v;
-            s.P[j * N + i] = v;
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+            if (ti0[rd] < 0 || ti0[rd] == N) continue;
+            const int i0 = ti0[rd], j0 = tj0[rd];
+            double ti[M][TS], kj[M][TS];
+#pragma unroll
+            for (int a = 0; a < M; ++a)
+#pragma unroll
+                for (int b = 0; b < TS; ++b) {
+                    ti[a][b] = s.T21[a * N + i0 + b];
+                    double kv = 0.0;
+#pragma unroll
+                    for (int c = 0; c < M; ++c) kv = fma(Si[a][c], s.T21[c * N + j0 + b], kv);
+                    kj[a][b] = kv;
+                }
+#pragma unroll
+            for (int a = 0; a < TS; ++a)
+#pragma unroll
+                for (int b = 0; b < TS; ++b) {
+                    if (i0 == j0 && b < a) continue;   // diagonal tile: upper part only
+                    double v = acc[rd][a][b] + Qt[(i0 + a) * N + j0 + b];
+#pragma unroll
+                    for (int c = 0; c < M; ++c) v = fma(-ti[c][a], kj[c][b], v);
+                    s.P[(i0 + a) * N + j0 + b] = v;
+                    s.P[(j0 + b) * N + i0 + a] = v;
+                }
         }
         __syncwarp();
     }
@@ -387,21 +518,31 @@ __device__ void riccati_factor(const Slab<CF> &s, const StageOps &ops, const QPD
 
 // ---------------------------------------------------------------------------------------------------------
 // Vector sweeps: backward (costate) then forward (rollout).  POLISH selects the linear control term.
-// Writes Uo always, Xo if WRITE_X.
+// Writes Uo always, Xo if WRITE_X.  The vector handed to the mat-vec alternates between two buffers, so one
+// warp sync per stage is enough.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF, bool POLISH, bool WRITE_X>
-__device__ void riccati_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, double rho_half, int lane) {
+template <class CF, bool FUSED>
+__device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
+                                           bool POLISH, bool WRITE_X, int lane) {
     constexpr int N = CF::N, M = CF::M;
-    double p = (lane < N) ? -qp.qlinf[lane] : 0.0;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
+    const bool act = lane < N;
+    double p = act ? -qp.qlinf[lane] : 0.0;
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double *Bt = s.B + t * N * M;
-        const double v = (lane < N) ? s.dv[t * N + lane] + p : 0.0;
-        if (lane < N) s.va[lane] = v;
+        double *vec = (t & 1) ? s.vb : s.va;
+        const double v = act ? s.dv[t * N + lane] + p : 0.0;
+        if (act) vec[lane] = v;
         __syncwarp();
         double g[M];
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = warp_sum(lane < N ? Bt[lane * M + i] * v : 0.0);
+        for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * v : 0.0;
+        warp_sum_vec<M>(g, lane);
+        const double atv = cmatvec<CF, true>(ops, phi_t, t, vec, lane);
         const double *Rt = qp.R + t * qp.r_stride;
 #pragma unroll
         for (int i = 0; i < M; ++i) {
@@ -425,7 +566,6 @@ __device__ void riccati_solve(const Slab<CF> &s, const StageOps &ops, const QPDa
             }
             g[i] -= h;
         }
-        const double atv = apply_AT<CF>(ops, phi_t, t, s.va, lane);
         double kkv[M];
 #pragma unroll
         for (int a = 0; a < M; ++a) {
@@ -437,26 +577,31 @@ __device__ void riccati_solve(const Slab<CF> &s, const StageOps &ops, const QPDa
 #pragma unroll
             for (int a = 0; a < M; ++a) s.kk[t * M + a] = kkv[a];
         }
-        if (lane < N) {
+        if (act) {
             double pn = atv - qp.qlin[t * N + lane];
 #pragma unroll
             for (int a = 0; a < M; ++a) pn = fma(-s.K[(t * M + a) * N + lane], g[a], pn);
             p = pn;
         }
-        __syncwarp();
     }
+    __syncwarp();
     // forward
-    double x = (lane < N) ? s.x0[lane] : 0.0;
-    if (WRITE_X && lane < N) s.Xo[lane] = x;
+    double x = act ? s.x0[lane] : 0.0;
+    if (WRITE_X && act) s.Xo[lane] = x;
     for (int t = 0; t < H; ++t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double *Bt = s.B + t * N * M;
-        if (lane < N) s.va[lane] = x;
+        double *vec = (t & 1) ? s.vb : s.va;
+        if (act) vec[lane] = x;
         __syncwarp();
         double u[M];
 #pragma unroll
+        for (int a = 0; a < M; ++a) u[a] = act ? s.K[(t * M + a) * N + lane] * x : 0.0;
+        warp_sum_vec<M>(u, lane);
+        const double ax = cmatvec<CF, false>(ops, phi_t, t, vec, lane);
+#pragma unroll
         for (int a = 0; a < M; ++a) {
-            u[a] = -warp_sum(lane < N ? s.K[(t * M + a) * N + lane] * x : 0.0) - s.kk[t * M + a];
+            u[a] = -u[a] - s.kk[t * M + a];
             if (POLISH) {
                 const int mk = s.mask[t * M + a];
                 if (mk) u[a] = mk == 1 ? box_lo(s, qp.sat, t, a) : box_hi(s, qp.sat, t, a);
@@ -466,16 +611,15 @@ __device__ void riccati_solve(const Slab<CF> &s, const StageOps &ops, const QPDa
 #pragma unroll
             for (int a = 0; a < M; ++a) s.Uo[t * M + a] = u[a];
         }
-        const double ax = apply_A<CF>(ops, phi_t, t, s.va, lane);
-        if (lane < N) {
+        if (act) {
             double xn = ax + s.D[t * N + lane];
 #pragma unroll
             for (int a = 0; a < M; ++a) xn = fma(Bt[lane * M + a], u[a], xn);
             x = xn;
             if (WRITE_X) s.Xo[(t + 1) * N + lane] = x;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // (Qbar v)[lane] for v in shared memory
@@ -497,9 +641,13 @@ __device__ __forceinline__ double apply_Q(const double *Qm, int q_diag, const do
 // Adjoint gradient of the condensed cost at (Xo, Uo) -> s.kk[t*M+i] (re-used as scratch); returns max |grad|.
 //   lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};  lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}
 // ---------------------------------------------------------------------------------------------------------
-template <class CF>
-__device__ double adjoint_gradient(const Slab<CF> &s, const StageOps &ops, const QPData &qp, int H, int lane) {
+template <class CF, bool FUSED>
+__device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, int lane) {
     constexpr int N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
     if (lane < N) s.vb[lane] = s.Xo[H * N + lane] - qp.r[H * N + lane];
     __syncwarp();
     double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.vb, lane);
@@ -535,13 +683,26 @@ __device__ double adjoint_gradient(const Slab<CF> &s, const StageOps &ops, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The QP: ADMM blocks (warp-vote convergence) + active-set polish with KKT certificate.
+// The QP (optimize.py:12-60).  Two building blocks share the Riccati kernels:
+//   * ADMM on the control box (u = z, z in [lo, hi]); u-update = equality-constrained LQ problem solved exactly by
+//     the time-varying Riccati recursion; convergence by warp vote over each lane's slice of the residuals.
+//   * primal-dual active set ("polish"): controls in the working set are pinned to their bound and folded into
+//     the dynamics, one masked Riccati factor + solve gives the equality-constrained optimum, and an adjoint
+//     gradient certifies the KKT conditions (multiplier signs on pinned controls, feasibility of free ones) or
+//     updates the set.
+// Tight mode (polish = 1): the working set is warm-started from the previous solve's (z, y) -- the previous SQP
+// iterate or the shifted previous MPC step -- and the active-set rounds run first; an ADMM block (which needs no
+// guess) is the fallback that re-seeds the set when the rounds do not certify.  admm_first = 1 always runs the ADMM
+// block before the rounds.  polish = 0 is plain ADMM to residual eps (OSQP-equivalent mode).
 // In: slab {B, D, phi, x0, lo0, hi0, z, y(warm)}.  Out: Xo, Uo; z, y updated.  Returns status 0 / 2 / 3.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF>
-__device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp, const QPSet &set, int H, int lane,
-                        Counters &cnt) {
+template <class CF, bool FUSED>
+__device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, const QPSet &set, int lane, Counters &cnt) {
     constexpr int N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
     const int HM = H * M;
     const double rho_half = 0.5 * set.rho;
     // clip the warm start into the current box
@@ -550,40 +711,35 @@ __device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp
         s.z[e] = fmin(fmax(s.z[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
     }
     __syncwarp();
-    riccati_factor<CF>(s, ops, qp, H, rho_half, false, lane);
-    cnt.factor++;
     cnt.solves++;
     double eps = set.eps;
     int status = 0;
-    bool admm_factor_valid = true;
+    bool run_admm = !set.polish || set.admm_first;
     for (;;) {
-        if (!admm_factor_valid) {
-            riccati_factor<CF>(s, ops, qp, H, rho_half, false, lane);
+        if (run_admm) {
+            riccati_factor<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, lane);
             cnt.factor++;
-            admm_factor_valid = true;
-        }
-        for (int it = 0; it < set.max_admm; ++it) {
-            if (set.polish) riccati_solve<CF, false, false>(s, ops, qp, H, rho_half, lane);
-            else riccati_solve<CF, false, true>(s, ops, qp, H, rho_half, lane);
-            cnt.admm++;
-            bool bad = false;
-            for (int e = lane; e < HM; e += 32) {
-                const int t = e / M, i = e % M;
-                const double u = s.Uo[e], zo = s.z[e];
-                const double uh = set.alpha * u + (1.0 - set.alpha) * zo;
-                const double zn = fmin(fmax(uh + s.y[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
-                s.y[e] += uh - zn;
-                s.z[e] = zn;
-                bad |= !(fabs(u - zn) < eps) || !(set.rho * fabs(zn - zo) < eps);
+            for (int it = 0; it < set.max_admm; ++it) {
+                riccati_solve<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, !set.polish, lane);
+                cnt.admm++;
+                bool bad = false;
+                for (int e = lane; e < HM; e += 32) {
+                    const int t = e / M, i = e % M;
+                    const double u = s.Uo[e], zo = s.z[e];
+                    const double uh = set.alpha * u + (1.0 - set.alpha) * zo;
+                    const double zn = fmin(fmax(uh + s.y[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+                    s.y[e] += uh - zn;
+                    s.z[e] = zn;
+                    bad |= !(fabs(u - zn) < eps) || !(set.rho * fabs(zn - zo) < eps);
+                }
+                __syncwarp();
+                if (!__any_sync(FULL, bad)) break;   // warp vote: every lane's slice of the residuals is below eps
             }
-            __syncwarp();
-            if (!__any_sync(FULL, bad)) break;   // warp vote: every lane's slice of the residuals is below eps
         }
         if (!set.polish) {
             // OSQP-equivalent mode: report the feasible iterate z and its rollout
             for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
             __syncwarp();
-            // rollout with u = z: reuse the forward pass by a plain model rollout
             double x = (lane < N) ? s.x0[lane] : 0.0;
             if (lane < N) s.Xo[lane] = x;
             for (int t = 0; t < H; ++t) {
@@ -601,7 +757,7 @@ __device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp
             }
             break;
         }
-        // ---- polish: primal-dual active set seeded by the ADMM estimate
+        // ---- working set from the (z, y) estimate: at a bound with the multiplier pushing outwards
         for (int e = lane; e < HM; e += 32) {
             const int t = e / M, i = e % M;
             const double zz = s.z[e], yy = s.y[e];
@@ -613,12 +769,11 @@ __device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp
         __syncwarp();
         bool certified = false;
         for (int round = 0; round < set.max_polish; ++round) {
-            riccati_factor<CF>(s, ops, qp, H, 0.0, true, lane);
-            admm_factor_valid = false;
+            riccati_factor<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
             cnt.factor++;
             cnt.polish++;
-            riccati_solve<CF, true, true>(s, ops, qp, H, 0.0, lane);
-            const double gmax = adjoint_gradient<CF>(s, ops, qp, H, lane);
+            riccati_solve<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, true, lane);
+            const double gmax = adjoint_gradient<CF, FUSED>(sr, ops_in, qp_in, lane);
             const double gs = fmax(1.0, gmax);
             bool changed = false;
             for (int e = lane; e < HM; e += 32) {
@@ -647,14 +802,19 @@ __device__ int qp_solve(const Slab<CF> &s, const StageOps &ops, const QPData &qp
             }
         }
         if (certified) {
+            // warm start of the next solve: z = u*, y = the (scaled) multipliers of the pinned controls
+            const double inv_rho = 1.0 / set.rho;
             for (int e = lane; e < HM; e += 32) {
                 const int t = e / M, i = e % M;
                 s.z[e] = fmin(fmax(s.Uo[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+                s.y[e] = s.mask[e] ? -s.kk[e] * inv_rho : 0.0;
             }
             __syncwarp();
             break;
         }
-        eps *= 0.1;
+        // not certified: (re)seed with an ADMM block at a tighter tolerance
+        if (run_admm) eps *= 0.1;
+        run_admm = true;
         if (eps < 1e-10) {
             status = 2;   // could not certify: report the ADMM iterate (reference: solver warning -> exit code 2)
             for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
@@ -696,9 +856,12 @@ __device__ double qp_objective(const Slab<CF> &s, const QPData &qp, int H, int l
 // Linearisation of the bilinear model along (Xg, Ug): fills phi, B, D  (linearize.py:50-70).
 //   B_t[:, i] = sum_k pow[k][i] * prod_l u_l^(pow[k][l] - [l == i]) * (N_k x_t);  D_t = -B_t u_t.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF>
-__device__ void linearize(const Slab<CF> &s, const StageOps &model, const int *pow, int H, int lane) {
+template <class CF, bool FUSED>
+__device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, const int *pow, int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps model = localize<FUSED>(model_in);
+    const int H = sr.H;
     const int p = model.nblk - 1;
     for (int t = 0; t < H; ++t) {
         // monomials and derivative weights: lane k < p computes its own
@@ -766,9 +929,12 @@ __device__ void linearize(const Slab<CF> &s, const StageOps &model, const int *p
 // X arrays here are [t][N] realified; r = qp.r.  Z index zeta -> (t, k): part = zeta / (C*(H+1)),
 // rem = zeta % (C*(H+1)), state = rem / (H+1), t = rem % (H+1), k = part*C + state.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF>
-__device__ void line_search(const Slab<CF> &s, const QPData &qp, int H, int lane, double &alpha, double &step) {
+template <class CF, bool FUSED>
+__device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int lane, double &alpha, double &step) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
     double num = 0.0, den = 0.0, nrm = 0.0;
     const int H1 = H + 1;
     for (int tau = 0; tau <= H; ++tau) {
@@ -871,7 +1037,7 @@ __device__ __forceinline__ double2 cmm(const double2 *A, const double2 *B, int d
 
 // U = expm(-i H dt) for Hermitian-or-not H (d x d) by scaling and squaring of a degree-16 Taylor polynomial.
 // Hm, T0, T1: shared scratch [d*d] double2 each.  Result left in T0.  All 32 lanes must call.
-__device__ void expm_minus_i(const double2 *Hm, double dt, int d, double2 *G, double2 *T0, double2 *T1, int lane) {
+__device__ __noinline__ void expm_minus_i(const double2 *Hm, double dt, int d, double2 *G, double2 *T0, double2 *T1, int lane) {
     const int dd = d * d;
     const int i = lane / d, j = lane % d;
     const bool act = lane < dd;
@@ -929,7 +1095,7 @@ __device__ void expm_minus_i(const double2 *Hm, double dt, int d, double2 *G, do
 }
 
 // rho <- U rho U^dagger ; rho in shared (double2 [dd]), U in shared; tmp scratch
-__device__ void conjugate(double2 *rho, const double2 *U, int d, double2 *tmp, int lane) {
+__device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, double2 *tmp, int lane) {
     const int dd = d * d;
     const int i = lane / d, j = lane % d;
     const bool act = lane < dd;

@@ -203,7 +203,7 @@ struct MpcArgs {
 };
 
 template <class CF>
-__global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
+__global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
     extern __shared__ double2 smem2[];
     double *smem = reinterpret_cast<double *>(smem2);
@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
     for (int e = threadIdx.x; e < (a.nblk - 1) * M; e += blockDim.x) pow[e] = a.powers[e];
     __syncthreads();
 
-    Slab<CF> s;
-    Slab<CF>::layout(&s, smem + a.shared_doubles + (size_t)warp * a.slab_doubles, H, a.nblk, cmax(dd, C));
+    const SlabRef sr = {a.shared_doubles + warp * a.slab_doubles, H, a.nblk, cmax(dd, C)};
+    const Slab<CF> s = slab_view<CF>(sr);
     double2 *xcur = reinterpret_cast<double2 *>(s.xcur);
     double2 *xmeas = reinterpret_cast<double2 *>(s.xmeas);
     double2 *scr2 = reinterpret_cast<double2 *>(s.scr);
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
     model.blocks = blocks;
     model.nblk = a.nblk;
     model.stage_stride = 0;
+    model.soff = 0;
 
     int *work = reinterpret_cast<int *>(a.tab + L.flags + 1);
     const int q_diag = a.tab[L.flags] != 0.0;
@@ -310,6 +311,9 @@ __global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
                 qp.Rub = a.tab + L.Rub + (size_t)w0 * M;
                 qp.sat = a.sat;
                 qp.q_diag = q_diag;
+                qp.Q_soff = 2 * a.nblk * C * C;
+                qp.Qf_soff = qp.Q_soff + N * N;
+                qp.R_soff = qp.Qf_soff + N * N;
 
                 // measured state -> model space: the QP's initial condition (mpc.py:187)
                 lift_state<CF>(a.external_plant ? M4Q_LIFT_IDENTITY : a.lift_mode, d, xcur, s.x0, lane);
@@ -329,8 +333,8 @@ __global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
                 int n_iter = 0;
                 bool done = false;
                 while (!done && n_iter < a.max_iter) {
-                    linearize<CF>(s, model, pow, H, lane);                      // mpc.py:175
-                    const int status = qp_solve<CF>(s, model, qp, a.set, H, lane, cnt);   // mpc.py:189
+                    linearize<CF, true>(sr, model, pow, lane);                  // mpc.py:175
+                    const int status = qp_solve<CF, true>(sr, model, qp, a.set, lane, cnt);   // mpc.py:189
                     if (status != 0) {
                         exit_code = status;
                         break;
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(512) mpc_kernel(const MpcArgs a) {
                         done = true;
                     } else {
                         double stp;
-                        line_search<CF>(s, qp, H, lane, alpha, stp);            // mpc.py:215
+                        line_search<CF, true>(sr, qp, lane, alpha, stp);        // mpc.py:215
                         done = stp < 1e-4;                                      // mpc.py:224
                     }
                     for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = fma(alpha, s.Xo[e] - s.Xg[e], s.Xg[e]);
@@ -490,15 +494,15 @@ struct QpArgs {
 };
 
 template <class CF>
-__global__ void __launch_bounds__(512) qp_kernel(const QpArgs a) {
+__global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
     extern __shared__ double2 smem2[];
     double *smem = reinterpret_cast<double *>(smem2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    Slab<CF> s;
-    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, 1, C);
+    const SlabRef sr = {warp * a.slab_doubles, H, 1, C};
+    const Slab<CF> s = slab_view<CF>(sr);
 
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         double *ws = a.ws + k * qp_ws_doubles(N, M, H);
@@ -575,6 +579,7 @@ __global__ void __launch_bounds__(512) qp_kernel(const QpArgs a) {
         ops.blocks = a.A_ls + (size_t)k * H * C * C;
         ops.nblk = 1;
         ops.stage_stride = C * C;
+        ops.soff = 0;
         QPData qp;
         qp.Q = wQ;
         qp.q_stride = N * N;
@@ -588,8 +593,9 @@ __global__ void __launch_bounds__(512) qp_kernel(const QpArgs a) {
         qp.Rub = wRub;
         qp.sat = a.sat;
         qp.q_diag = 0;
+        qp.Q_soff = qp.Qf_soff = qp.R_soff = 0;
         Counters cnt = {0, 0, 0, 0};
-        int status = qp_solve<CF>(s, ops, qp, a.set, H, lane, cnt);
+        int status = qp_solve<CF, false>(sr, ops, qp, a.set, lane, cnt);
         const double obj = qp_objective<CF>(s, qp, H, lane);
         if (!isfinite(obj)) status = 3;   // mpc.py:200
         double2 *Xo = a.X_out + (size_t)k * C * (H + 1);
@@ -626,19 +632,20 @@ struct LinArgs {
 };
 
 template <class CF>
-__global__ void __launch_bounds__(512) linearize_kernel(const LinArgs a) {
+__global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs a) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
     extern __shared__ double2 smem2[];
     double *smem = reinterpret_cast<double *>(smem2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    Slab<CF> s;
-    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, a.nblk, C);
+    const SlabRef sr = {warp * a.slab_doubles, H, a.nblk, C};
+    const Slab<CF> s = slab_view<CF>(sr);
     StageOps model;
     model.blocks = a.A_blocks;
     model.nblk = a.nblk;
     model.stage_stride = 0;
+    model.soff = 0;
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         const double2 *Xk = a.Xg + (size_t)k * C * (H + 1);
         const double *Uk = a.Ug + (size_t)k * M * H;
@@ -649,7 +656,7 @@ __global__ void __launch_bounds__(512) linearize_kernel(const LinArgs a) {
         }
         for (int e = lane; e < H * M; e += 32) s.Ug[e] = Uk[(e % M) * H + e / M];
         __syncwarp();
-        linearize<CF>(s, model, a.powers, H, lane);
+        linearize<CF, false>(sr, model, a.powers, lane);
         double2 *Ao = a.A_out + (size_t)k * H * C * C;
         double2 *Bo = a.B_out + (size_t)k * H * C * M;
         double2 *Do = a.D_out + (size_t)k * H * C;
@@ -712,15 +719,15 @@ struct LsArgs {
 };
 
 template <class CF>
-__global__ void __launch_bounds__(512) line_search_kernel(const LsArgs a) {
+__global__ void __launch_bounds__(CF::MAXW * 32) line_search_kernel(const LsArgs a) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
     extern __shared__ double2 smem2[];
     double *smem = reinterpret_cast<double *>(smem2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    Slab<CF> s;
-    Slab<CF>::layout(&s, smem + (size_t)warp * a.slab_doubles, H, 1, C);
+    const SlabRef sr = {warp * a.slab_doubles, H, 1, C};
+    const Slab<CF> s = slab_view<CF>(sr);
     QPData qp;
     qp.Q = a.ws;
     qp.q_stride = N * N;
@@ -732,6 +739,7 @@ __global__ void __launch_bounds__(512) line_search_kernel(const LsArgs a) {
     qp.qlin = qp.qlinf = qp.Rub = nullptr;
     qp.sat = 0.0;
     qp.q_diag = 0;
+    qp.Q_soff = qp.Qf_soff = qp.R_soff = 0;
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         const double2 *Xgk = a.Xg + (size_t)k * C * (H + 1), *Xok = a.Xo + (size_t)k * C * (H + 1);
         const double *Ugk = a.Ug + (size_t)k * M * H, *Uok = a.Uo + (size_t)k * M * H;
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(512) line_search_kernel(const LsArgs a) {
         }
         __syncwarp();
         double alpha, stp;
-        line_search<CF>(s, qp, H, lane, alpha, stp);
+        line_search<CF, false>(sr, qp, lane, alpha, stp);
         if (lane == 0) {
             a.alpha_out[k] = alpha;
             a.step_out[k] = stp;
@@ -891,6 +899,25 @@ __global__ void __launch_bounds__(256) fp64_fma_kernel(long long iters, double s
     if (sum == 123.456) out[0] = sum;
 }
 
+// fp64 tensor-core probe: mma.sync m8n8k4 f64 chains (DMMA), 8 independent accumulators per warp
+__global__ void __launch_bounds__(256) fp64_dmma_kernel(long long iters, double seed, double *out) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = seed + i;
+    const double a = 1.0 - 1e-12 + threadIdx.x * 1e-15, b = 0.25;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += c[i][0] + c[i][1];
+    if (sum == 123.456) out[0] = sum;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Launch geometry
 // ---------------------------------------------------------------------------------------------------------
@@ -908,13 +935,14 @@ static int device_props(int *sms, int *max_smem) {
 
 // warps per CTA: as many slabs as fit in shared memory (<= 16), grid = SMs * resident CTAs
 template <class KernelT>
-static int plan(KernelT kernel, int slab_doubles, int shared_doubles, long long n_units, bool have_device, Geometry *g) {
+static int plan(KernelT kernel, int max_warps, int slab_doubles, int shared_doubles, long long n_units, bool have_device,
+                Geometry *g) {
     int sms = 148, max_smem = 232448;
     if (have_device && device_props(&sms, &max_smem) != 0) return -1;
     const long long slab_b = (long long)slab_doubles * 8, shared_b = (long long)shared_doubles * 8;
     if (shared_b + slab_b > max_smem) return fail("horizon too long for the shared-memory slab of this (c, m) instantiation");
     int warps = (int)((max_smem - shared_b) / slab_b);
-    if (warps > 16) warps = 16;
+    if (warps > max_warps) warps = max_warps;
     // small slabs: prefer several CTAs per SM over one wide CTA so that the CTA-shared tables stay cheap to load
     g->warps = warps;
     g->smem = (int)(shared_b + (long long)warps * slab_b);
@@ -944,6 +972,7 @@ static QPSet qp_settings(const m4q_qp_settings *s) {
     q.eps = (s && s->eps > 0) ? s->eps : (q.polish ? 1e-2 : 1e-5);
     q.max_admm = (s && s->max_admm > 0) ? s->max_admm : 400;
     q.max_polish = (s && s->max_polish > 0) ? s->max_polish : 8;
+    q.admm_first = s ? s->admm_first : 0;
     return q;
 }
 
@@ -954,7 +983,7 @@ template <class CF> static int mpc_shared_doubles(int nblk) {
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
     const int dd = p->d * p->d;
     const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2);
-    return plan(mpc_kernel<CF>, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
+    return plan(mpc_kernel<CF>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
 }
 
 template <class CF>
@@ -1070,7 +1099,7 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
     M4Q_DISPATCH(c, m, {
         Geometry g;
         const int slab = rup(Slab<CF>::doubles(H, p + 1, CF::C), 2);
-        if (plan(linearize_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        if (plan(linearize_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
         linearize_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
     });
@@ -1116,7 +1145,7 @@ int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double
     M4Q_DISPATCH(c, m, {
         Geometry g;
         const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
-        if (plan(qp_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        if (plan(qp_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
         qp_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
     });
@@ -1150,7 +1179,7 @@ int m4q_line_search_batched(int64_t N, int32_t c, int32_t m, int32_t H, const do
     M4Q_DISPATCH(c, m, {
         Geometry g;
         const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
-        if (plan(line_search_kernel<CF>, slab, 0, N, true, &g) != 0) return -1;
+        if (plan(line_search_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
         line_search_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
     });
@@ -1251,6 +1280,12 @@ int m4q_hist_fidelity(int64_t N, const double *fidelity, double lo, double hi, i
 
 int m4q_fp64_fma_probe(int32_t ctas, int64_t iters, double *scratch, void *stream) {
     fp64_fma_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(iters, 0.5, scratch);
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int m4q_fp64_dmma_probe(int32_t ctas, int64_t iters, double *scratch, void *stream) {
+    fp64_dmma_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(iters, 0.5, scratch);
     M4Q_CUDA(cudaGetLastError());
     return 0;
 }
