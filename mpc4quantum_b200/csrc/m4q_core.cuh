@@ -23,43 +23,67 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 // ---------------------------------------------------------------------------------------------------------
 // Compile-time configuration for a (complex state dim, control dim) pair.
-// TR1 x TC1: register tile of W = P [A|B] (N x Q).  TS x TS: register tile of [A|B]^T W, of which only the
-// upper block triangle of the N x N part and the M control rows are computed (the product is symmetric).
-// ---------------------------------------------------------------------------------------------------------
+// The two dense products of a Riccati stage, W = P G and T = G^T W with G = [A_t | B_t] (N x Q), run on the fp64
+// tensor cores (mma.sync m8n8k4, "DMMA"): operands padded to NP = rup(N, 8) rows, QP = rup(Q, 8) columns and
+// KP = rup(N, 4) in the contraction; leading dimensions chosen so that the fragment loads are free of bank
+// conflicts (A-type loads: ld = 4 or 12 mod 16; B-type loads: ld = 8 mod 16).
 // MAXW: most warps (members) a CTA is ever launched with; it fixes the register budget (__launch_bounds__).
-template <int C_, int M_> struct Tiles { static constexpr int TR1 = 2, TC1 = 4, TS = 2, MAXW = 16; };
-template <> struct Tiles<4, 1>  { static constexpr int TR1 = 2, TC1 = 3, TS = 2, MAXW = 16; };
-template <> struct Tiles<9, 2>  { static constexpr int TR1 = 3, TC1 = 4, TS = 3, MAXW = 8; };
-template <> struct Tiles<8, 2>  { static constexpr int TR1 = 2, TC1 = 5, TS = 4, MAXW = 8; };
-template <> struct Tiles<16, 3> { static constexpr int TR1 = 4, TC1 = 9, TS = 4, MAXW = 4; };
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r - x % m) % m + m) % m; }
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };
+template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
 
 template <int C_, int M_> struct Cfg {
     static constexpr int C = C_, N = 2 * C_, M = M_, Q = N + M_;
-    using T = Tiles<C_, M_>;
-    static constexpr int TR1 = T::TR1, TC1 = T::TC1, TS = T::TS, MAXW = T::MAXW;
-    static_assert(N % TR1 == 0, "row tile of W must divide N");
-    static_assert(N % TS == 0, "tile of the symmetric product must divide N");
-    static_assert(TS >= M, "control rows must fit in one tile row");
-    // tiles of the symmetric product: upper block triangle of T11 plus one row of tiles for [T21 | T22]
-    static constexpr int NT = N / TS, NT11 = NT * (NT + 1) / 2, NT2 = cdiv(Q, TS), NTILES = NT11 + NT2;
-    static constexpr int ROUNDS = cdiv(NTILES, 32);
-    static constexpr int LD = rup(cmax(cmax(rup(Q, TC1), N + TS), rup(Q, TS)), 2);
+    static constexpr int MAXW = Tiles<C_, M_>::MAXW;
+    static constexpr int NP = rup(N, 8), QP = rup(Q, 8), KP = rup(N, 4);
+    static constexpr int MT = NP / 8, QT = QP / 8, KS = KP / 4;   // tile counts
+    static constexpr int LDP = cmin(next_mod(KP, 4, 16), next_mod(KP, 12, 16));
+    static constexpr int LDG = next_mod(QP, 8, 16);
+    static_assert(LDP >= Q && LDP % 2 == 0, "T11 and the control columns are staged in the P buffer");
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-private slab (offsets in doubles).  H is a run-time value.
+// Memory plan of one member (= one warp).
+//   * shared-memory slab: the Riccati scratch (P, [A|B], W), a 2-slot ring of stage records, the control
+//     trajectories and a few vectors -- 13 KB for the transmon, (almost) independent of the horizon, so that
+//     ~16 members are resident per SM;
+//   * L2-resident workspace in global memory (one per resident warp, re-used member after member): the
+//     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t], then the state trajectories
+//     Xg, Xo [(H+1) N].  Records are written with plain stores where they are produced (factor: K, S^-1, dv;
+//     linearisation: B, D) and streamed back one stage ahead of their use through the ring with cp.async
+//     (LDGSTS, 16-byte chunks), so the sweeps never wait on L2.
 // ---------------------------------------------------------------------------------------------------------
+template <class CF> struct Rec {
+    static constexpr int K = 0;                                  // [M][N]
+    static constexpr int SINV = K + rup(CF::M * CF::N, 2);       // [M][M]
+    static constexpr int DV = SINV + rup(CF::M * CF::M, 2);      // [N]
+    static constexpr int B = DV + CF::N;                         // [N][M]
+    static constexpr int D = B + rup(CF::N * CF::M, 2);          // [N]
+    static constexpr int SIZE = D + CF::N;
+    static_assert(B % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
+};
+template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
+    return H * Rec<CF>::SIZE + 2 * (H + 1) * CF::N;
+}
+
 template <class CF> struct Slab {
-    double *P, *AB, *W, *T21, *S, *K, *B, *D, *Sinv, *dv, *kk, *phi, *Xg, *Ug, *Xo, *Uo, *z, *y, *x0, *va, *vb,
-        *lo0, *hi0, *xcur, *xmeas, *scr;
+    double *P, *AB, *W, *T21, *S, *ring, *kk, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *lo0, *hi0, *xcur, *xmeas, *scr;
     int *mask;
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
         return layout(nullptr, nullptr, H, nblk, dd);
     }
-    // dd = plant state length in complex numbers (d*d); scr holds 4 complex d x d matrices for expm
+    // scratch of the linearisation (2 x [p][M] derivative weights) and of the plant step (4 complex d x d):
+    // aliases W, which is only live inside the Riccati factor
+    __host__ __device__ static bool scratch_fits(int nblk, int dd) {
+        return cmax(8 * dd, 2 * CF::M * nblk) <= CF::NP * CF::LDG;
+    }
+    // dd = plant state length in complex numbers (d*d)
     __host__ __device__ static int layout(Slab *s, double *base, int H, int nblk, int dd) {
-        constexpr int N = CF::N, M = CF::M, LD = CF::LD;
+        constexpr int N = CF::N, M = CF::M;
         int o = 0;
         auto take = [&](double **dst, int cnt) {
             if (s) *dst = base + o;
@@ -67,21 +91,16 @@ template <class CF> struct Slab {
         };
         Slab dummy;
         Slab *q = s ? s : &dummy;
-        take(&q->P, N * N);
-        take(&q->AB, N * LD);
-        take(&q->W, N * LD);
+        take(&q->P, CF::NP * CF::LDP);    // P_{t+1}, zero padded
+        take(&q->AB, CF::KP * CF::LDG);   // G = [A_t | B~_t], zero padded
+        take(&q->W, CF::NP * CF::LDG);    // W = P G
+        q->scr = q->W;
         take(&q->T21, M * N);
         take(&q->S, M * M);
-        take(&q->K, H * M * N);
-        take(&q->B, H * N * M);
-        take(&q->D, H * N);
-        take(&q->Sinv, H * M * M);
-        take(&q->dv, H * N);
+        take(&q->ring, 2 * Rec<CF>::SIZE);
         take(&q->kk, H * M);
         take(&q->phi, H * nblk);
-        take(&q->Xg, (H + 1) * N);
         take(&q->Ug, H * M);
-        take(&q->Xo, (H + 1) * N);
         take(&q->Uo, H * M);
         take(&q->z, H * M);
         take(&q->y, H * M);
@@ -92,7 +111,6 @@ template <class CF> struct Slab {
         take(&q->hi0, M);
         take(&q->xcur, 2 * dd);
         take(&q->xmeas, 2 * dd);
-        take(&q->scr, cmax(8 * dd, 4 * M * MAXBLK));
         double *mk = nullptr;
         take(&mk, cdiv(H * M, 2));
         if (s) s->mask = reinterpret_cast<int *>(mk);
@@ -107,7 +125,8 @@ template <class CF> struct Slab {
 // ---------------------------------------------------------------------------------------------------------
 // The large device functions below are __noinline__ (one copy each: the hot code has to stay resident in the
 // instruction cache) and therefore re-derive every shared-memory pointer from the dynamic shared-memory base, so
-// that the compiler keeps emitting LDS/STS instead of generic loads.  A slab is named by its offset (in doubles).
+// that the compiler keeps emitting LDS/STS instead of generic loads.  A slab is named by its offset (in doubles);
+// ws is the member's workspace (global memory in the fused loop and the QP kernel).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double *dyn_smem() {
     extern __shared__ double2 m4q_dyn_smem[];
@@ -115,11 +134,30 @@ __device__ __forceinline__ double *dyn_smem() {
 }
 struct SlabRef {
     int off, H, nblk, dd;
+    double *ws;
 };
 template <class CF> __device__ __forceinline__ Slab<CF> slab_view(const SlabRef &r) {
     Slab<CF> s;
     Slab<CF>::layout(&s, dyn_smem() + r.off, r.H, r.nblk, r.dd);
     return s;
+}
+template <class CF> __device__ __forceinline__ double *ws_rec(const SlabRef &r, int t) { return r.ws + t * Rec<CF>::SIZE; }
+template <class CF> __device__ __forceinline__ double *ws_Xg(const SlabRef &r) { return r.ws + r.H * Rec<CF>::SIZE; }
+template <class CF> __device__ __forceinline__ double *ws_Xo(const SlabRef &r) {
+    return r.ws + r.H * Rec<CF>::SIZE + (r.H + 1) * CF::N;
+}
+
+// cp.async (LDGSTS): 16 bytes global -> shared, L2 only
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(__cvta_generic_to_global(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// stream doubles [first, first + count) of a record into a ring slot (first, count even); one group per call
+__device__ __forceinline__ void prefetch_rec(double *slot, const double *rec, int first, int count, int lane) {
+    for (int c = lane; c < (count >> 1); c += 32) cp_async16(slot + first + 2 * c, rec + first + 2 * c);
+    cp_async_commit();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -203,37 +241,12 @@ template <int M> __device__ __forceinline__ void warp_sum_vec(double (&g)[M], in
     }
 }
 
-// out[i][j] = sum_k X[k][i] * Y[k][j], register tile TR x TC per lane, tiles round-robin over lanes.
-template <int TR, int TC, int NK, int NI, int NJ, class Sink>
-__device__ __forceinline__ void xty(const double *__restrict__ X, int ldx, const double *__restrict__ Y, int ldy,
-                                    int lane, Sink sink) {
-    constexpr int nti = cdiv(NI, TR), ntj = cdiv(NJ, TC);
-    for (int tile = lane; tile < nti * ntj; tile += 32) {
-        const int i0 = (tile / ntj) * TR, j0 = (tile % ntj) * TC;
-        double acc[TR][TC];
-#pragma unroll
-        for (int a = 0; a < TR; ++a)
-#pragma unroll
-            for (int b = 0; b < TC; ++b) acc[a][b] = 0.0;
-        const double *xp = X + i0, *yp = Y + j0;
-#pragma unroll(NK % 3 == 0 ? 3 : 2)
-        for (int k = 0; k < NK; ++k) {
-            double xv[TR], yv[TC];
-#pragma unroll
-            for (int a = 0; a < TR; ++a) xv[a] = xp[k * ldx + a];
-#pragma unroll
-            for (int b = 0; b < TC; ++b) yv[b] = yp[k * ldy + b];
-#pragma unroll
-            for (int a = 0; a < TR; ++a)
-#pragma unroll
-                for (int b = 0; b < TC; ++b) acc[a][b] = fma(xv[a], yv[b], acc[a][b]);
-        }
-#pragma unroll
-        for (int a = 0; a < TR; ++a)
-#pragma unroll
-            for (int b = 0; b < TC; ++b)
-                if (i0 + a < NI && j0 + b < NJ) sink(i0 + a, j0 + b, acc[a][b]);
-    }
+// D (8x8) += A (8x4, row) * B (4x8, col) on the fp64 tensor cores.  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+// D[l/4][2*(l%4) + {0, 1}].
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d[0]), "+d"(d[1])
+        : "d"(a), "d"(b));
 }
 
 // inverse of a small symmetric positive definite matrix held in registers (Gauss-Jordan, no pivoting)
@@ -325,55 +338,42 @@ template <class CF> __device__ __forceinline__ double box_hi(const Slab<CF> &s, 
 
 // ---------------------------------------------------------------------------------------------------------
 // Riccati matrix sweep.  masked: controls with mask != 0 are pinned to their bound (polish), rho_half = 0.
-// Produces K_t, S_t^-1, dv_t = P_{t+1} (D_t + B_fixed b) for all stages.
+// Produces K_t, S_t^-1, dv_t = P_{t+1} (D_t + B_fixed b) for all stages (written to the stage records).
 //
-// Per stage, with G = [A_t | B~_t] (N x Q):  W = P G  (3x4 register tiles), then T = G^T W, which is symmetric:
-// only the upper block triangle of T11 = A^T P A and the M control rows [T21 | T22] are computed, one TS x TS
-// tile per lane, accumulators kept in registers across the warp sync that publishes T21 / T22, and the update
+// Per stage, with G = [A_t | B~_t] (N x Q):  W = P G, then T = G^T W, both as DMMA tile products with the
+// accumulators in registers.  T is symmetric: only its upper block triangle is computed; the lanes that hold the
+// control columns publish T12 (= T21^T) and T22, and after one warp sync the update
 //   P_t = Qbar_t + T11 - T21^T S^-1 T21,   S = R + rho/2 + T22
-// is applied in the tile epilogue and mirrored, so P stays exactly symmetric and T11 never touches memory.
+// is applied to the accumulator fragments and mirrored, so P stays exactly symmetric and T11 never touches memory.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
                                             bool masked, int lane) {
-    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q, LD = CF::LD, TS = CF::TS;
+    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q;
+    constexpr int NP = CF::NP, KP = CF::KP, LDP = CF::LDP, LDG = CF::LDG, MT = CF::MT, QT = CF::QT, KS = CF::KS;
+    using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
     const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
-    constexpr int NT = CF::NT, NT11 = CF::NT11, NTILES = CF::NTILES, ROUNDS = CF::ROUNDS;
-    // tile coordinates of this lane (fixed for the whole sweep)
-    int ti0[ROUNDS], tj0[ROUNDS];
-#pragma unroll
-    for (int rd = 0; rd < ROUNDS; ++rd) {
-        const int tile = lane + 32 * rd;
-        if (tile < NT11) {   // unrank (bi <= bj)
-            int bi = 0, rem = tile;
-            while (rem >= NT - bi) {
-                rem -= NT - bi;
-                ++bi;
-            }
-            ti0[rd] = bi * TS;
-            tj0[rd] = (bi + rem) * TS;
-        } else if (tile < NTILES) {
-            ti0[rd] = N;
-            tj0[rd] = (tile - NT11) * TS;
-        } else {
-            ti0[rd] = -1;
-            tj0[rd] = 0;
-        }
+    const int g8 = lane >> 2, c4 = lane & 3;   // fragment coordinates of this lane
+    // P <- Qf with zero padding; G, W padding rows / columns zeroed once (never written afterwards)
+    for (int e = lane; e < NP * LDP; e += 32) {
+        const int i = e / LDP, j = e % LDP;
+        s.P[e] = (i < N && j < N) ? qp.Qf[i * N + j] : 0.0;
     }
-    for (int e = lane; e < N * N; e += 32) s.P[e] = qp.Qf[e];
-    for (int e = lane; e < N * (LD - Q); e += 32) {   // zero the padding columns once
-        const int k = e / (LD - Q), j = Q + e % (LD - Q);
-        s.AB[k * LD + j] = 0.0;
-        s.W[k * LD + j] = 0.0;
-    }
-    __syncwarp();
+    for (int e = lane; e < KP * LDG; e += 32) s.AB[e] = 0.0;
+    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), R_::B, R_::SIZE - R_::B, lane);
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
-        // realified A_t into AB[:, 0:N]
+        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        double *rec = ws_rec<CF>(sr, t);
+        cp_async_wait_all();
+        __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
+        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), R_::B, R_::SIZE - R_::B, lane);
+        // realified A_t into G[:, 0:N]
+#pragma unroll 1
         for (int e = lane; e < C * C; e += 32) {
             const int r = e / C, j = e % C;
             double ar = 0.0, ai = 0.0;
@@ -382,20 +382,20 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 ar = fma(phi_t[kb], v.x, ar);
                 ai = fma(phi_t[kb], v.y, ai);
             }
-            s.AB[r * LD + j] = ar;
-            s.AB[r * LD + C + j] = -ai;
-            s.AB[(C + r) * LD + j] = ai;
-            s.AB[(C + r) * LD + C + j] = ar;
+            s.AB[r * LDG + j] = ar;
+            s.AB[r * LDG + C + j] = -ai;
+            s.AB[(C + r) * LDG + j] = ai;
+            s.AB[(C + r) * LDG + C + j] = ar;
         }
-        // B~ into AB[:, N:Q] and D~ into va
-        const double *Bt = s.B + t * N * M;
+        // B~ into G[:, N:Q] and D~ into va
+        const double *Bt = slot + R_::B;
         for (int e = lane; e < N * M; e += 32) {
             const int k = e / M, i = e % M;
             const bool fixed = masked && s.mask[t * M + i] != 0;
-            s.AB[k * LD + N + i] = fixed ? 0.0 : Bt[e];
+            s.AB[k * LDG + N + i] = fixed ? 0.0 : Bt[e];
         }
         if (lane < N) {
-            double dt = s.D[t * N + lane];
+            double dt = slot[R_::D + lane];
             if (masked) {
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
@@ -410,46 +410,81 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int j = 0; j < N; j += 2) {
-                a0 = fma(s.P[j * N + lane], s.va[j], a0);
-                a1 = fma(s.P[(j + 1) * N + lane], s.va[j + 1], a1);
+                a0 = fma(s.P[j * LDP + lane], s.va[j], a0);
+                a1 = fma(s.P[(j + 1) * LDP + lane], s.va[j + 1], a1);
             }
-            s.dv[t * N + lane] = a0 + a1;
+            rec[R_::DV + lane] = a0 + a1;
         }
-        // W = P [A | B~]
-        xty<CF::TR1, CF::TC1, N, N, Q>(s.P, N, s.AB, LD, lane, [&](int i, int j, double v) { s.W[i * LD + j] = v; });
+        // ---- W = P G : MT x QT tiles, KS k-steps (rolled: the hot code has to fit the instruction cache)
+        {
+            double w[MT][QT][2];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < QT; ++ni) w[mi][ni][0] = w[mi][ni][1] = 0.0;
+            const double *pa = s.P + g8 * LDP + c4;      // A fragment: P[mi*8 + g8][ks*4 + c4]
+            const double *gb = s.AB + c4 * LDG + g8;     // B fragment: G[ks*4 + c4][ni*8 + g8]
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ++ks, pa += 4, gb += 4 * LDG) {
+                double af[MT], bf[QT];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) af[mi] = pa[mi * 8 * LDP];
+#pragma unroll
+                for (int ni = 0; ni < QT; ++ni) bf[ni] = gb[ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < QT; ++ni) dmma(w[mi][ni], af[mi], bf[ni]);
+            }
+            double2 *wd = reinterpret_cast<double2 *>(s.W + g8 * LDG + 2 * c4);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < QT; ++ni) wd[(mi * 8 * LDG + ni * 8) >> 1] = make_double2(w[mi][ni][0], w[mi][ni][1]);
+        }
         __syncwarp();
-        // T tiles: acc[a][b] = sum_k G[k][i0 + a] W[k][j0 + b]
-        double acc[ROUNDS][TS][TS];
+        // ---- T = G^T W, upper block triangle: tile (mi <= ni) holds T[mi*8 + g8][ni*8 + 2*c4 + {0,1}].
+        // T11 goes into the P buffer (P_{t+1} is dead: it was the A operand of the first product), the control
+        // columns T12 = T21^T and T22 into their own small arrays.
+        {
+            double tt[QT][QT][2];
 #pragma unroll
-        for (int rd = 0; rd < ROUNDS; ++rd) {
+            for (int mi = 0; mi < QT; ++mi)
 #pragma unroll
-            for (int a = 0; a < TS; ++a)
+                for (int ni = mi; ni < QT; ++ni) tt[mi][ni][0] = tt[mi][ni][1] = 0.0;
+            const double *ga = s.AB + c4 * LDG + g8;     // A fragment: G^T[mi*8 + g8][ks*4 + c4] = G[ks*4 + c4][mi*8 + g8]
+            const double *wb = s.W + c4 * LDG + g8;      // B fragment: W[ks*4 + c4][ni*8 + g8]
+#pragma unroll 1
+            for (int ks = 0; ks < KS; ++ks, ga += 4 * LDG, wb += 4 * LDG) {
+                double af[QT], bf[QT];
 #pragma unroll
-                for (int b = 0; b < TS; ++b) acc[rd][a][b] = 0.0;
-            if (ti0[rd] < 0) continue;
-            const double *xp = s.AB + ti0[rd], *yp = s.W + tj0[rd];
-#pragma unroll(N % 3 == 0 ? 3 : 2)
-            for (int k = 0; k < N; ++k) {
-                double xv[TS], yv[TS];
+                for (int mi = 0; mi < QT; ++mi) af[mi] = ga[mi * 8];
 #pragma unroll
-                for (int a = 0; a < TS; ++a) xv[a] = xp[k * LD + a];
+                for (int ni = 0; ni < QT; ++ni) bf[ni] = wb[ni * 8];
 #pragma unroll
-                for (int b = 0; b < TS; ++b) yv[b] = yp[k * LD + b];
+                for (int mi = 0; mi < QT; ++mi)
 #pragma unroll
-                for (int a = 0; a < TS; ++a)
-#pragma unroll
-                    for (int b = 0; b < TS; ++b) acc[rd][a][b] = fma(xv[a], yv[b], acc[rd][a][b]);
+                    for (int ni = mi; ni < QT; ++ni) dmma(tt[mi][ni], af[mi], bf[ni]);
             }
-            if (ti0[rd] == N) {   // control rows: publish T21 and T22
 #pragma unroll
-                for (int a = 0; a < M; ++a)
+            for (int mi = 0; mi < QT; ++mi)
 #pragma unroll
-                    for (int b = 0; b < TS; ++b) {
-                        const int j = tj0[rd] + b;
-                        if (j < N) s.T21[a * N + j] = acc[rd][a][b];
-                        else if (j < Q) s.S[a * M + (j - N)] = acc[rd][a][b];
+                for (int ni = mi; ni < QT; ++ni) {
+                    const int i = mi * 8 + g8, j = ni * 8 + 2 * c4;   // N and j even: the pair (j, j+1) is on one side
+                    if (j < N) {
+                        if (i < N) *reinterpret_cast<double2 *>(s.P + i * LDP + j) = make_double2(tt[mi][ni][0], tt[mi][ni][1]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            if (j + e >= Q) continue;
+                            if (i < N) s.T21[(j + e - N) * N + i] = tt[mi][ni][e];
+                            else if (i <= j + e) {
+                                s.S[(i - N) * M + (j + e - N)] = tt[mi][ni][e];
+                                s.S[(j + e - N) * M + (i - N)] = tt[mi][ni][e];
+                            }
+                        }
                     }
-            }
+                }
         }
         __syncwarp();
         // S = R~ + rho/2 + B~^T P B~ ; invert (every lane redundantly, M <= 3)
@@ -461,7 +496,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll
             for (int b = 0; b < M; ++b) {
                 const bool fb = masked && s.mask[t * M + b] != 0;
-                double v = 0.5 * (s.S[a * M + b] + s.S[b * M + a]);
+                double v = s.S[a * M + b];
                 if (fa || fb) v = (a == b) ? 1.0 : 0.0;
                 else v += Rt[a * M + b] + (a == b ? rho_half : 0.0);
                 Sm[a][b] = v;
@@ -472,7 +507,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll
             for (int a = 0; a < M; ++a)
 #pragma unroll
-                for (int b = 0; b < M; ++b) s.Sinv[(t * M + a) * M + b] = Si[a][b];
+                for (int b = 0; b < M; ++b) rec[R_::SINV + a * M + b] = Si[a][b];
         }
         if (lane < N) {
 #pragma unroll
@@ -480,64 +515,63 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 double kv = 0.0;
 #pragma unroll
                 for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + lane], kv);
-                s.K[(t * M + a) * N + lane] = kv;
+                rec[R_::K + a * N + lane] = kv;
             }
         }
-        // P_t = Qbar_t + T11 - T21^T K on the upper block triangle, mirrored
+        // P_t = Qbar_t + T11 - T21^T S^-1 T21, in place on the upper triangle and mirrored
         const double *Qt = qp.Q + t * qp.q_stride;
+#pragma unroll 1
+        for (int e = lane; e < N * N; e += 32) {
+            const int i = e / N, j = e % N;
+            if (i > j) continue;
+            double v = s.P[i * LDP + j] + Qt[e];
 #pragma unroll
-        for (int rd = 0; rd < ROUNDS; ++rd) {
-            if (ti0[rd] < 0 || ti0[rd] == N) continue;
-            const int i0 = ti0[rd], j0 = tj0[rd];
-            double ti[M][TS], kj[M][TS];
+            for (int a = 0; a < M; ++a) {
+                double kv = 0.0;
 #pragma unroll
-            for (int a = 0; a < M; ++a)
-#pragma unroll
-                for (int b = 0; b < TS; ++b) {
-                    ti[a][b] = s.T21[a * N + i0 + b];
-                    double kv = 0.0;
-#pragma unroll
-                    for (int c = 0; c < M; ++c) kv = fma(Si[a][c], s.T21[c * N + j0 + b], kv);
-                    kj[a][b] = kv;
-                }
-#pragma unroll
-            for (int a = 0; a < TS; ++a)
-#pragma unroll
-                for (int b = 0; b < TS; ++b) {
-                    if (i0 == j0 && b < a) continue;   // diagonal tile: upper part only
-                    double v = acc[rd][a][b] + Qt[(i0 + a) * N + j0 + b];
-#pragma unroll
-                    for (int c = 0; c < M; ++c) v = fma(-ti[c][a], kj[c][b], v);
-                    s.P[(i0 + a) * N + j0 + b] = v;
-                    s.P[(j0 + b) * N + i0 + a] = v;
-                }
+                for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + j], kv);
+                v = fma(-s.T21[a * N + i], kv, v);
+            }
+            s.P[i * LDP + j] = v;
+            s.P[j * LDP + i] = v;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Vector sweeps: backward (costate) then forward (rollout).  POLISH selects the linear control term.
-// Writes Uo always, Xo if WRITE_X.  The vector handed to the mat-vec alternates between two buffers, so one
-// warp sync per stage is enough.
+// Writes Uo always, Xo (workspace) if WRITE_X.  Stage records arrive through the ring one stage ahead; the two
+// per-lane scalars needed before the stage's only warp sync (dv_t, qlin_t) are register-prefetched.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
                                            bool POLISH, bool WRITE_X, int lane) {
     constexpr int N = CF::N, M = CF::M;
+    using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
     const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const bool act = lane < N;
+    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), 0, R_::SIZE, lane);
     double p = act ? -qp.qlinf[lane] : 0.0;
+    double dv_n = act ? ws_rec<CF>(sr, H - 1)[R_::DV + lane] : 0.0;
+    double ql_n = act ? qp.qlin[(H - 1) * N + lane] : 0.0;
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
-        const double *Bt = s.B + t * N * M;
+        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        const double *Bt = slot + R_::B;
         double *vec = (t & 1) ? s.vb : s.va;
-        const double v = act ? s.dv[t * N + lane] + p : 0.0;
+        const double v = dv_n + p, ql = ql_n;
         if (act) vec[lane] = v;
+        if (t > 0 && act) {
+            dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
+            ql_n = qp.qlin[(t - 1) * N + lane];
+        }
+        cp_async_wait_all();
         __syncwarp();
+        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), 0, R_::SIZE, lane);
         double g[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * v : 0.0;
@@ -571,32 +605,36 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
         for (int a = 0; a < M; ++a) {
             kkv[a] = 0.0;
 #pragma unroll
-            for (int b = 0; b < M; ++b) kkv[a] = fma(s.Sinv[(t * M + a) * M + b], g[b], kkv[a]);
+            for (int b = 0; b < M; ++b) kkv[a] = fma(slot[R_::SINV + a * M + b], g[b], kkv[a]);
         }
         if (lane == 0) {
 #pragma unroll
             for (int a = 0; a < M; ++a) s.kk[t * M + a] = kkv[a];
         }
         if (act) {
-            double pn = atv - qp.qlin[t * N + lane];
+            double pn = atv - ql;
 #pragma unroll
-            for (int a = 0; a < M; ++a) pn = fma(-s.K[(t * M + a) * N + lane], g[a], pn);
+            for (int a = 0; a < M; ++a) pn = fma(-slot[R_::K + a * N + lane], g[a], pn);
             p = pn;
         }
     }
-    __syncwarp();
-    // forward
+    __syncwarp();   // kk complete; va/vb free again
+    // forward: record 0 is still in slot 0
+    double *Xo = ws_Xo<CF>(sr);
     double x = act ? s.x0[lane] : 0.0;
-    if (WRITE_X && act) s.Xo[lane] = x;
+    if (WRITE_X && act) Xo[lane] = x;
     for (int t = 0; t < H; ++t) {
         const double *phi_t = s.phi + t * ops.nblk;
-        const double *Bt = s.B + t * N * M;
+        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        const double *Bt = slot + R_::B;
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) vec[lane] = x;
+        cp_async_wait_all();
         __syncwarp();
+        if (t + 1 < H) prefetch_rec(s.ring + ((t + 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t + 1), 0, R_::SIZE, lane);
         double u[M];
 #pragma unroll
-        for (int a = 0; a < M; ++a) u[a] = act ? s.K[(t * M + a) * N + lane] * x : 0.0;
+        for (int a = 0; a < M; ++a) u[a] = act ? slot[R_::K + a * N + lane] * x : 0.0;
         warp_sum_vec<M>(u, lane);
         const double ax = cmatvec<CF, false>(ops, phi_t, t, vec, lane);
 #pragma unroll
@@ -612,11 +650,11 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
             for (int a = 0; a < M; ++a) s.Uo[t * M + a] = u[a];
         }
         if (act) {
-            double xn = ax + s.D[t * N + lane];
+            double xn = ax + slot[R_::D + lane];
 #pragma unroll
             for (int a = 0; a < M; ++a) xn = fma(Bt[lane * M + a], u[a], xn);
             x = xn;
-            if (WRITE_X) s.Xo[(t + 1) * N + lane] = x;
+            if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
     }
     __syncwarp();
@@ -640,31 +678,44 @@ __device__ __forceinline__ double apply_Q(const double *Qm, int q_diag, const do
 // ---------------------------------------------------------------------------------------------------------
 // Adjoint gradient of the condensed cost at (Xo, Uo) -> s.kk[t*M+i] (re-used as scratch); returns max |grad|.
 //   lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};  lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}
+// B_t through the ring, x_t - r_t register-prefetched; vectors double-buffered (va/vb, and W as scratch).
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, int lane) {
     constexpr int N = CF::N, M = CF::M;
+    using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
     const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
-    if (lane < N) s.vb[lane] = s.Xo[H * N + lane] - qp.r[H * N + lane];
+    const bool act = lane < N;
+    const double *Xo = ws_Xo<CF>(sr);
+    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), R_::B, R_::SIZE - R_::B, lane);
+    double xd_n = act ? Xo[(H - 1) * N + lane] - qp.r[(H - 1) * N + lane] : 0.0;
+    if (act) s.W[lane] = Xo[H * N + lane] - qp.r[H * N + lane];
     __syncwarp();
-    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.vb, lane);
+    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.W, lane);
     double gmax = 0.0;
+    __syncwarp();
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
-        const double *Bt = s.B + t * N * M;
+        const double *Bt = s.ring + (t & 1) * R_::SIZE + R_::B;
         const double *Rt = qp.R + t * qp.r_stride;
-        __syncwarp();
-        if (lane < N) {
-            s.va[lane] = lam;
-            s.vb[lane] = s.Xo[t * N + lane] - qp.r[t * N + lane];
+        double *lamv = (t & 1) ? s.vb : s.va;
+        double *xdv = s.W + (t & 1) * N;
+        const double xd = xd_n;
+        if (act) {
+            lamv[lane] = lam;
+            xdv[lane] = xd;
+            if (t > 0) xd_n = Xo[(t - 1) * N + lane] - qp.r[(t - 1) * N + lane];
         }
+        cp_async_wait_all();
         __syncwarp();
+        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), R_::B, R_::SIZE - R_::B, lane);
         double g[M];
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = warp_sum(lane < N ? Bt[lane * M + i] * lam : 0.0);
+        for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * lam : 0.0;
+        warp_sum_vec<M>(g, lane);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
 #pragma unroll
@@ -675,8 +726,8 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_
 #pragma unroll
             for (int i = 0; i < M; ++i) s.kk[t * M + i] = g[i];
         }
-        const double atl = apply_AT<CF>(ops, phi_t, t, s.va, lane);
-        lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, s.vb, lane);
+        const double atl = cmatvec<CF, true>(ops, phi_t, t, lamv, lane);
+        lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, xdv, lane);
     }
     __syncwarp();
     return gmax;
@@ -740,18 +791,20 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             // OSQP-equivalent mode: report the feasible iterate z and its rollout
             for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
             __syncwarp();
+            double *Xo = ws_Xo<CF>(sr);
             double x = (lane < N) ? s.x0[lane] : 0.0;
-            if (lane < N) s.Xo[lane] = x;
+            if (lane < N) Xo[lane] = x;
             for (int t = 0; t < H; ++t) {
+                const double *rec = ws_rec<CF>(sr, t);
                 if (lane < N) s.va[lane] = x;
                 __syncwarp();
                 const double ax = apply_A<CF>(ops, s.phi + t * ops.nblk, t, s.va, lane);
                 if (lane < N) {
-                    double xn = ax + s.D[t * N + lane];
+                    double xn = ax + rec[Rec<CF>::D + lane];
 #pragma unroll
-                    for (int a = 0; a < M; ++a) xn = fma(s.B[(t * N + lane) * M + a], s.Uo[t * M + a], xn);
+                    for (int a = 0; a < M; ++a) xn = fma(rec[Rec<CF>::B + lane * M + a], s.Uo[t * M + a], xn);
                     x = xn;
-                    s.Xo[(t + 1) * N + lane] = x;
+                    Xo[(t + 1) * N + lane] = x;
                 }
                 __syncwarp();
             }
@@ -825,19 +878,25 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     // non-finite result -> reference exit code 3 (mpc.py:200-203)
     bool nonfinite = false;
     for (int e = lane; e < HM; e += 32) nonfinite |= !isfinite(s.Uo[e]);
-    for (int e = lane; e < (H + 1) * N; e += 32) nonfinite |= !isfinite(s.Xo[e]);
+    {
+        const double *Xo = ws_Xo<CF>(sr);
+        for (int e = lane; e < (H + 1) * N; e += 32) nonfinite |= !isfinite(Xo[e]);
+    }
     if (__any_sync(FULL, nonfinite)) status = 3;
     return status;
 }
 
 // objective value sum (x-r)^T Q (x-r) + (u-ub)^T R (u-ub)  (optimize.py:34-35, :54; no 1/2)
 template <class CF>
-__device__ double qp_objective(const Slab<CF> &s, const QPData &qp, int H, int lane) {
+__device__ double qp_objective(const SlabRef &sr, const QPData &qp, int lane) {
     constexpr int N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const int H = sr.H;
+    const double *Xo = ws_Xo<CF>(sr);
     double acc = 0.0;
     for (int t = 0; t <= H; ++t) {
         __syncwarp();
-        if (lane < N) s.vb[lane] = s.Xo[t * N + lane] - qp.r[t * N + lane];
+        if (lane < N) s.vb[lane] = Xo[t * N + lane] - qp.r[t * N + lane];
         __syncwarp();
         const double qv = apply_Q<CF>(t == H ? qp.Qf : qp.Q + t * qp.q_stride, qp.q_diag, s.vb, lane);
         if (lane < N) acc = fma(qv, s.vb[lane], acc);
@@ -853,19 +912,34 @@ __device__ double qp_objective(const Slab<CF> &s, const QPData &qp, int H, int l
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Linearisation of the bilinear model along (Xg, Ug): fills phi, B, D  (linearize.py:50-70).
+// Linearisation of the bilinear model along (Xg, Ug): fills phi (slab) and B, D (stage records)
+// (linearize.py:50-70).
 //   B_t[:, i] = sum_k pow[k][i] * prod_l u_l^(pow[k][l] - [l == i]) * (N_k x_t);  D_t = -B_t u_t.
+// x_t comes from the workspace one stage ahead (register prefetch); the vector and the derivative weights are
+// double-buffered, so one warp sync per stage.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, const int *pow, int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
+    using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
     const StageOps model = localize<FUSED>(model_in);
     const int H = sr.H;
     const int p = model.nblk - 1;
+    const double *Xg = ws_Xg<CF>(sr);
+    const bool act = lane < N;
+    const bool im = lane >= C;
+    const int r = im ? lane - C : lane;
+    const double sgn = im ? 1.0 : -1.0;
+    double x_n = act ? Xg[lane] : 0.0;
     for (int t = 0; t < H; ++t) {
+        double *dco = s.scr + (t & 1) * (p * M);   // [p][M]
+        double *vec = (t & 1) ? s.vb : s.va;
+        if (act) {
+            vec[lane] = x_n;
+            if (t + 1 < H) x_n = Xg[(t + 1) * N + lane];
+        }
         // monomials and derivative weights: lane k < p computes its own
-        double *dco = s.scr;   // [p][M]
         if (lane < p) {
             double phi = 1.0;
             double dw[M];
@@ -888,46 +962,58 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
 #pragma unroll
             for (int i = 0; i < M; ++i) dco[lane * M + i] = dw[i];
         }
-        if (lane == 0) s.phi[t * model.nblk] = 1.0;
+        if (lane == 31) s.phi[t * model.nblk] = 1.0;
         __syncwarp();
-        if (lane < N) {
-            const int r = lane % C;
-            const bool im = lane >= C;
-            const double *x = s.Xg + t * N;
+        if (act) {
+            const double *xp = vec + (im ? C : 0), *xq = vec + (im ? 0 : C);
+            double pv[C], qv[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                pv[j] = xp[j];
+                qv[j] = xq[j];
+            }
             double b[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) b[i] = 0.0;
-            for (int kb = 1; kb <= p; ++kb) {
-                const double2 *blk = model.blocks + (kb * C + r) * C;
-                double s0 = 0.0, s1 = 0.0;
+            const double2 *blk = model.blocks + (C + r) * C;
+            for (int kb = 1; kb <= p; ++kb, blk += C * C) {
+                double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
-                    const double2 mij = blk[j];
-                    s0 = fma(im ? mij.y : mij.x, x[j], s0);
-                    s1 = fma(im ? mij.x : -mij.y, x[C + j], s1);
+                    const double2 m = blk[j];
+                    if (j & 1) {
+                        p1 = fma(m.x, pv[j], p1);
+                        q1 = fma(m.y, qv[j], q1);
+                    } else {
+                        p0 = fma(m.x, pv[j], p0);
+                        q0 = fma(m.y, qv[j], q0);
+                    }
                 }
-                const double y = s0 + s1;
+                const double y = fma(sgn, q0 + q1, p0 + p1);
 #pragma unroll
                 for (int i = 0; i < M; ++i) b[i] = fma(dco[(kb - 1) * M + i], y, b[i]);
             }
+            double *rec = ws_rec<CF>(sr, t);
             double d = 0.0;
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                s.B[(t * N + lane) * M + i] = b[i];
+                rec[R_::B + lane * M + i] = b[i];
                 d = fma(-b[i], s.Ug[t * M + i], d);
             }
-            s.D[t * N + lane] = d;
+            rec[R_::D + lane] = d;
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Line search (mpc.py:101-125): alpha = -(M (Zg - Zt)) . DZ / (DZ . M DZ), step = |alpha| ||DZ||_2 with
 // M = blockdiag(Qbar_0..Qbar_H, [[R,0],[0,R]]_0..) in TIME-major order while Z is the STATE-major flattening
 // [Re X.ravel(), Im X.ravel(), Re U.ravel(), Im U.ravel()] of X [c][H+1], U [m][H].  Reproduced as is.
-// X arrays here are [t][N] realified; r = qp.r.  Z index zeta -> (t, k): part = zeta / (C*(H+1)),
-// rem = zeta % (C*(H+1)), state = rem / (H+1), t = rem % (H+1), k = part*C + state.
+// X arrays here are [t][N] realified (workspace); r = qp.r.  Z index zeta <-> (t, k):
+//   part = zeta / (C*(H+1)), rem = zeta % (C*(H+1)), state = rem / (H+1), t = rem % (H+1), k = part*C + state,
+// and zeta belongs to metric block tau = zeta / N, row zeta % N.  Diagonal costs: one coalesced pass in memory
+// order; full costs: block by block with gathers.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int lane, double &alpha, double &step) {
@@ -935,28 +1021,38 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
     const Slab<CF> s = slab_view<CF>(sr);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
+    const double *Xg = ws_Xg<CF>(sr), *Xo = ws_Xo<CF>(sr);
     double num = 0.0, den = 0.0, nrm = 0.0;
     const int H1 = H + 1;
-    for (int tau = 0; tau <= H; ++tau) {
-        double e_k = 0.0, d_k = 0.0;
-        if (lane < N) {
-            const int zeta = tau * N + lane;
-            const int part = zeta / (C * H1), rem = zeta % (C * H1);
-            const int st = rem / H1, t = rem % H1;
-            const int idx = t * N + part * C + st;
-            const double xg = s.Xg[idx];
-            e_k = xg - qp.r[idx];
-            d_k = s.Xo[idx] - xg;
+    if (qp.q_diag) {
+#pragma unroll 4
+        for (int e = lane; e < H1 * N; e += 32) {
+            const int t = e / N, k = e % N;
+            const int part = k / C, st = k % C;
+            const int zeta = (part * C + st) * H1 + t;
+            const int tau = zeta / N, row = zeta % N;
+            const double *Qt = (tau == H) ? qp.Qf : qp.Q + tau * qp.q_stride;
+            const double qd = Qt[row * N + row];
+            const double xg = Xg[e];
+            const double e_k = xg - qp.r[e], d_k = Xo[e] - xg;
             nrm = fma(d_k, d_k, nrm);
+            num = fma(qd * e_k, d_k, num);
+            den = fma(qd * d_k, d_k, den);
         }
-        const double *Qt = (tau == H) ? qp.Qf : qp.Q + tau * qp.q_stride;
-        if (qp.q_diag) {
+    } else {
+        for (int tau = 0; tau <= H; ++tau) {
+            double e_k = 0.0, d_k = 0.0;
             if (lane < N) {
-                const double qd = Qt[lane * N + lane];
-                num = fma(qd * e_k, d_k, num);
-                den = fma(qd * d_k, d_k, den);
+                const int zeta = tau * N + lane;
+                const int part = zeta / (C * H1), rem = zeta % (C * H1);
+                const int st = rem / H1, t = rem % H1;
+                const int idx = t * N + part * C + st;
+                const double xg = Xg[idx];
+                e_k = xg - qp.r[idx];
+                d_k = Xo[idx] - xg;
+                nrm = fma(d_k, d_k, nrm);
             }
-        } else {
+            const double *Qt = (tau == H) ? qp.Qf : qp.Q + tau * qp.q_stride;
             __syncwarp();
             if (lane < N) {
                 s.va[lane] = e_k;
@@ -1016,6 +1112,7 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
         alpha = -num / den;
         step = fabs(alpha) * sqrt(nrm);
     }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------

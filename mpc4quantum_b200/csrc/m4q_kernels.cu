@@ -8,6 +8,7 @@
 #include "../../include/m4q.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -199,6 +200,7 @@ struct MpcArgs {
     int *exit_code, *steps_done, *qp_count, *counters;
     double *fidelity;
     double *state;
+    double *ws;   // L2-resident workspaces, one per resident warp (ws_doubles<CF>(H) each)
     int slab_doubles, shared_doubles;
 };
 
@@ -227,8 +229,11 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     for (int e = threadIdx.x; e < (a.nblk - 1) * M; e += blockDim.x) pow[e] = a.powers[e];
     __syncthreads();
 
-    const SlabRef sr = {a.shared_doubles + warp * a.slab_doubles, H, a.nblk, cmax(dd, C)};
+    const SlabRef sr = {a.shared_doubles + warp * a.slab_doubles, H, a.nblk, cmax(dd, C),
+                        a.ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * ws_doubles<CF>(H)};
     const Slab<CF> s = slab_view<CF>(sr);
+    double *Xg = ws_Xg<CF>(sr);
+    const double *Xo = ws_Xo<CF>(sr);
     double2 *xcur = reinterpret_cast<double2 *>(s.xcur);
     double2 *xmeas = reinterpret_cast<double2 *>(s.xmeas);
     double2 *scr2 = reinterpret_cast<double2 *>(s.scr);
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
             }
             __syncwarp();
             lift_state<CF>(a.external_plant ? M4Q_LIFT_IDENTITY : a.lift_mode, d, xcur, s.x0, lane);
-            for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = s.x0[e % N];   // mpc.py:141
+            for (int e = lane; e < (H + 1) * N; e += 32) Xg[e] = s.x0[e % N];     // mpc.py:141
             for (int e = lane; e < H * M; e += 32) {                              // mpc.py:142
                 s.Ug[e] = 0.0;
                 s.z[e] = 0.0;
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         } else {
             const double *st = a.state + (size_t)k * persist;
             int o = 0;
-            for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = st[o + e];
+            for (int e = lane; e < (H + 1) * N; e += 32) Xg[e] = st[o + e];
             o += (H + 1) * N;
             for (int e = lane; e < H * M; e += 32) {
                 s.Ug[e] = st[o + e];
@@ -347,7 +352,11 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                         line_search<CF, true>(sr, qp, lane, alpha, stp);        // mpc.py:215
                         done = stp < 1e-4;                                      // mpc.py:224
                     }
-                    for (int e = lane; e < (H + 1) * N; e += 32) s.Xg[e] = fma(alpha, s.Xo[e] - s.Xg[e], s.Xg[e]);
+#pragma unroll 4
+                    for (int e = lane; e < (H + 1) * N; e += 32) {
+                        const double xg = Xg[e];
+                        Xg[e] = fma(alpha, Xo[e] - xg, xg);
+                    }
                     for (int e = lane; e < H * M; e += 32) s.Ug[e] = fma(alpha, s.Uo[e] - s.Ug[e], s.Ug[e]);
                     __syncwarp();
                     ++n_iter;
@@ -402,8 +411,10 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
 
                 // shift the guesses (mpc.py:271-272) and, with them, the ADMM warm start
                 // (each lane moves its own component through time: no cross-lane hazard)
-                if (lane < N)
-                    for (int t = 0; t < H; ++t) s.Xg[t * N + lane] = s.Xg[(t + 1) * N + lane];
+                if (lane < N) {
+#pragma unroll 4
+                    for (int t = 0; t < H; ++t) Xg[t * N + lane] = Xg[(t + 1) * N + lane];
+                }
                 if (lane < M)
                     for (int t = 0; t + 1 < H; ++t) {
                         s.Ug[t * M + lane] = s.Ug[(t + 1) * M + lane];
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         if (a.state) {
             double *st = a.state + (size_t)k * persist;
             int o = 0;
-            for (int e = lane; e < (H + 1) * N; e += 32) st[o + e] = s.Xg[e];
+            for (int e = lane; e < (H + 1) * N; e += 32) st[o + e] = Xg[e];
             o += (H + 1) * N;
             for (int e = lane; e < H * M; e += 32) {
                 st[o + e] = s.Ug[e];
@@ -475,8 +486,9 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
 // Stand-alone horizon QP: one warp per instance, dense per-stage operators read from global memory.
 // Workspace per instance (doubles): Q [(H+1) N N] | R [H M M] | r [(H+1) N] | qlin [(H+1) N] | ub [H M] | Rub [H M]
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ inline long long qp_ws_doubles(int N, int M, int H) {
-    return (long long)(H + 1) * N * N + (long long)H * M * M + 2LL * (H + 1) * N + 2LL * H * M;
+template <class CF> __host__ __device__ inline long long qp_ws_doubles(int H) {
+    constexpr int N = CF::N, M = CF::M;
+    return (long long)(H + 1) * N * N + (long long)H * M * M + 2LL * (H + 1) * N + 2LL * rup(H * M, 2) + ws_doubles<CF>(H);
 }
 
 struct QpArgs {
@@ -501,13 +513,14 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    const SlabRef sr = {warp * a.slab_doubles, H, 1, C};
+    SlabRef sr = {warp * a.slab_doubles, H, 1, C, nullptr};
     const Slab<CF> s = slab_view<CF>(sr);
 
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
-        double *ws = a.ws + k * qp_ws_doubles(N, M, H);
+        double *ws = a.ws + k * qp_ws_doubles<CF>(H);
         double *wQ = ws, *wR = wQ + (size_t)(H + 1) * N * N, *wr = wR + H * M * M, *wql = wr + (H + 1) * N,
-               *wub = wql + (H + 1) * N, *wRub = wub + H * M;
+               *wub = wql + (H + 1) * N, *wRub = wub + rup(H * M, 2);
+        sr.ws = wRub + rup(H * M, 2);
         const double2 *Qk = a.Q_ls + (size_t)k * (H + 1) * C * C;
         const double *Rk = a.R_ls + (size_t)k * H * M * M;
         const double2 *Xb = a.X_bm + (size_t)k * C * (H + 1);
@@ -546,12 +559,12 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         for (int e = lane; e < H * N * M; e += 32) {
             const int t = e / (N * M), rem = e % (N * M), kk = rem / M, i = rem % M;
             const double2 v = Bk[((size_t)t * C + kk % C) * M + i];
-            s.B[e] = kk < C ? v.x : v.y;
+            ws_rec<CF>(sr, t)[Rec<CF>::B + rem] = kk < C ? v.x : v.y;
         }
         for (int e = lane; e < H * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 v = Dk[(size_t)t * C + kk % C];
-            s.D[e] = kk < C ? v.x : v.y;
+            ws_rec<CF>(sr, t)[Rec<CF>::D + kk] = kk < C ? v.x : v.y;
         }
         for (int e = lane; e < H; e += 32) s.phi[e] = 1.0;
         for (int e = lane; e < H * M; e += 32) {
@@ -596,13 +609,14 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         qp.Q_soff = qp.Qf_soff = qp.R_soff = 0;
         Counters cnt = {0, 0, 0, 0};
         int status = qp_solve<CF, false>(sr, ops, qp, a.set, lane, cnt);
-        const double obj = qp_objective<CF>(s, qp, H, lane);
+        const double obj = qp_objective<CF>(sr, qp, lane);
         if (!isfinite(obj)) status = 3;   // mpc.py:200
         double2 *Xo = a.X_out + (size_t)k * C * (H + 1);
         double *Uo = a.U_out + (size_t)k * M * H;
+        const double *wXo = ws_Xo<CF>(sr);
         for (int e = lane; e < C * (H + 1); e += 32) {
             const int kk = e / (H + 1), t = e % (H + 1);
-            Xo[e] = make_double2(s.Xo[t * N + kk], s.Xo[t * N + C + kk]);
+            Xo[e] = make_double2(wXo[t * N + kk], wXo[t * N + C + kk]);
         }
         for (int e = lane; e < M * H; e += 32) Uo[e] = s.Uo[(e % H) * M + e / H];
         if (lane == 0) {
@@ -639,8 +653,10 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    const SlabRef sr = {warp * a.slab_doubles, H, a.nblk, C};
+    const int slab_only = rup(Slab<CF>::doubles(H, a.nblk, C), 2);
+    const SlabRef sr = {warp * a.slab_doubles, H, a.nblk, C, smem + (size_t)warp * a.slab_doubles + slab_only};
     const Slab<CF> s = slab_view<CF>(sr);
+    double *wXg = ws_Xg<CF>(sr);
     StageOps model;
     model.blocks = a.A_blocks;
     model.nblk = a.nblk;
@@ -652,7 +668,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 v = Xk[(kk % C) * (H + 1) + t];
-            s.Xg[e] = kk < C ? v.x : v.y;
+            wXg[e] = kk < C ? v.x : v.y;
         }
         for (int e = lane; e < H * M; e += 32) s.Ug[e] = Uk[(e % M) * H + e / M];
         __syncwarp();
@@ -673,11 +689,13 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
         }
         for (int e = lane; e < H * C * M; e += 32) {
             const int t = e / (C * M), rem = e % (C * M), r = rem / M, i = rem % M;
-            Bo[e] = make_double2(s.B[(t * N + r) * M + i], s.B[(t * N + C + r) * M + i]);
+            const double *rec = ws_rec<CF>(sr, t);
+            Bo[e] = make_double2(rec[Rec<CF>::B + r * M + i], rec[Rec<CF>::B + (C + r) * M + i]);
         }
         for (int e = lane; e < H * C; e += 32) {
             const int t = e / C, r = e % C;
-            Do[e] = make_double2(s.D[t * N + r], s.D[t * N + C + r]);
+            const double *rec = ws_rec<CF>(sr, t);
+            Do[e] = make_double2(rec[Rec<CF>::D + r], rec[Rec<CF>::D + C + r]);
         }
         __syncwarp();
     }
@@ -726,8 +744,10 @@ __global__ void __launch_bounds__(CF::MAXW * 32) line_search_kernel(const LsArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int H = a.H;
-    const SlabRef sr = {warp * a.slab_doubles, H, 1, C};
+    const int slab_only = rup(Slab<CF>::doubles(H, 1, C), 2);
+    const SlabRef sr = {warp * a.slab_doubles, H, 1, C, smem + (size_t)warp * a.slab_doubles + slab_only};
     const Slab<CF> s = slab_view<CF>(sr);
+    double *wXg = ws_Xg<CF>(sr), *wXo = ws_Xo<CF>(sr);
     QPData qp;
     qp.Q = a.ws;
     qp.q_stride = N * N;
@@ -746,8 +766,8 @@ __global__ void __launch_bounds__(CF::MAXW * 32) line_search_kernel(const LsArgs
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 g = Xgk[(kk % C) * (H + 1) + t], o = Xok[(kk % C) * (H + 1) + t];
-            s.Xg[e] = kk < C ? g.x : g.y;
-            s.Xo[e] = kk < C ? o.x : o.y;
+            wXg[e] = kk < C ? g.x : g.y;
+            wXo[e] = kk < C ? o.x : o.y;
         }
         for (int e = lane; e < H * M; e += 32) {
             s.Ug[e] = Ugk[(e % M) * H + e / M];
@@ -943,6 +963,10 @@ static int plan(KernelT kernel, int max_warps, int slab_doubles, int shared_doub
     if (shared_b + slab_b > max_smem) return fail("horizon too long for the shared-memory slab of this (c, m) instantiation");
     int warps = (int)((max_smem - shared_b) / slab_b);
     if (warps > max_warps) warps = max_warps;
+    if (const char *ov = getenv("M4Q_MAX_WARPS")) {   // measurement aid: cap the members per CTA
+        const int w = atoi(ov);
+        if (w >= 1 && w < warps) warps = w;
+    }
     // small slabs: prefer several CTAs per SM over one wide CTA so that the CTA-shared tables stay cheap to load
     g->warps = warps;
     g->smem = (int)(shared_b + (long long)warps * slab_b);
@@ -982,6 +1006,7 @@ template <class CF> static int mpc_shared_doubles(int nblk) {
 
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
     const int dd = p->d * p->d;
+    if (!Slab<CF>::scratch_fits(p->p + 1, cmax(dd, CF::C))) return fail("model / plant too large for the slab scratch");
     const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2);
     return plan(mpc_kernel<CF>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
 }
@@ -993,6 +1018,8 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
     MpcArgs a = base;
     a.slab_doubles = g.slab_doubles;
     a.shared_doubles = g.shared_doubles;
+    // per-warp workspaces follow the shared tables (sized by m4q_mpc_table_bytes for the widest launch)
+    a.ws = a.tab + rup(TableLayout(CF::N, CF::M, p->n_targ).total, 2);
     build_tables<<<1, 256, 0, st>>>(CF::C, CF::M, p->n_targ, reinterpret_cast<const double2 *>(p->Q),
                                     reinterpret_cast<const double2 *>(p->Qf), p->R,
                                     reinterpret_cast<const double2 *>(p->X_targ), p->U_targ, a.tab);
@@ -1098,7 +1125,8 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
     a.D_out = (double2 *)D_out;
     M4Q_DISPATCH(c, m, {
         Geometry g;
-        const int slab = rup(Slab<CF>::doubles(H, p + 1, CF::C), 2);
+        if (!Slab<CF>::scratch_fits(p + 1, CF::C)) return fail("model too large for the slab scratch");
+        const int slab = rup(Slab<CF>::doubles(H, p + 1, CF::C), 2) + rup(ws_doubles<CF>(H), 2);
         if (plan(linearize_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
         linearize_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
@@ -1108,7 +1136,17 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
 }
 
 int64_t m4q_qp_workspace_bytes(int64_t N, int32_t c, int32_t m, int32_t H) {
-    return (int64_t)sizeof(double) * N * qp_ws_doubles(2 * c, m, H);
+    int64_t per = -1;
+    if (c == 4 && m == 1) per = qp_ws_doubles<Cfg<4, 1>>(H);
+    else if (c == 4 && m == 2) per = qp_ws_doubles<Cfg<4, 2>>(H);
+    else if (c == 9 && m == 2) per = qp_ws_doubles<Cfg<9, 2>>(H);
+    else if (c == 8 && m == 2) per = qp_ws_doubles<Cfg<8, 2>>(H);
+    else if (c == 16 && m == 3) per = qp_ws_doubles<Cfg<16, 3>>(H);
+    if (per < 0) {
+        fail("unsupported (c, m): no compiled instantiation");
+        return -1;
+    }
+    return (int64_t)sizeof(double) * N * per;
 }
 
 int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double *x_init, const double *X_bm,
@@ -1178,7 +1216,7 @@ int m4q_line_search_batched(int64_t N, int32_t c, int32_t m, int32_t H, const do
     a.ws = (const double *)workspace;
     M4Q_DISPATCH(c, m, {
         Geometry g;
-        const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
+        const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2) + rup(ws_doubles<CF>(H), 2);
         if (plan(line_search_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
         line_search_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
@@ -1197,7 +1235,16 @@ int64_t m4q_mpc_state_bytes(const m4q_mpc_problem *p, int64_t N) {
 
 int64_t m4q_mpc_table_bytes(const m4q_mpc_problem *p) {
     if (check_problem(p) != 0) return -1;
-    return (int64_t)sizeof(double) * TableLayout(2 * p->c, p->m, p->n_targ).total;
+    Geometry g;
+    int count = 0;
+    const bool have_device = cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+    if (!have_device) cudaGetLastError();
+    long long ws = 0;
+    M4Q_DISPATCH(p->c, p->m, {
+        if (mpc_geometry<CF>(p, 1LL << 40, have_device, &g) != 0) return -1;
+        ws = (long long)g.ctas * g.warps * ws_doubles<CF>(p->horizon);
+    });
+    return (int64_t)sizeof(double) * (rup(TableLayout(2 * p->c, p->m, p->n_targ).total, 2) + ws);
 }
 
 int m4q_mpc_launch_info(const m4q_mpc_problem *p, int32_t *warps_per_cta, int32_t *ctas, int32_t *smem_bytes) {
