@@ -70,7 +70,7 @@ template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
 }
 
 template <class CF> struct Slab {
-    double *P, *AB, *W, *T21, *S, *ring, *kk, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *lo0, *hi0, *xcur, *xmeas, *scr;
+    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *lo0, *hi0, *xcur, *xmeas, *scr;
     int *mask;
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
@@ -99,6 +99,7 @@ template <class CF> struct Slab {
         take(&q->S, M * M);
         take(&q->ring, 2 * Rec<CF>::SIZE);
         take(&q->kk, H * M);
+        take(&q->hl, H * M);
         take(&q->phi, H * nblk);
         take(&q->Ug, H * M);
         take(&q->Uo, H * M);
@@ -300,6 +301,7 @@ __device__ __forceinline__ double cmatvec(const StageOps &ops, const double *phi
     }
     const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + (TRANS ? r : r * C);
     double out = 0.0;
+#pragma unroll 1
     for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
         double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
@@ -377,6 +379,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
         for (int e = lane; e < C * C; e += 32) {
             const int r = e / C, j = e % C;
             double ar = 0.0, ai = 0.0;
+#pragma unroll 1
             for (int kb = 0; kb < ops.nblk; ++kb) {
                 const double2 v = blk0[kb * C * C + e];
                 ar = fma(phi_t[kb], v.x, ar);
@@ -540,9 +543,11 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Vector sweeps: backward (costate) then forward (rollout).  POLISH selects the linear control term.
-// Writes Uo always, Xo (workspace) if WRITE_X.  Stage records arrive through the ring one stage ahead; the two
-// per-lane scalars needed before the stage's only warp sync (dv_t, qlin_t) are register-prefetched.
+// Vector sweeps: backward (costate) then forward (rollout).  Writes Uo and, if WRITE_X, Xo (workspace).
+// POLISH: controls with mask != 0 are pinned to their bound; otherwise the ADMM linear term (mask must be 0).
+// A pre-pass folds both cases into one array hl: the linear term h of a free control, the bound of a pinned one.
+// Stage records arrive through the ring one stage ahead; the two per-lane scalars needed before the stage's only
+// warp sync (dv_t, qlin_t) are register-prefetched.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
@@ -555,13 +560,38 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
     const int H = sr.H;
     const bool act = lane < N;
     prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), 0, R_::SIZE, lane);
+#pragma unroll 1
+    for (int e = lane; e < H * M; e += 32) {
+        const int t = e / M, i = e % M;
+        const double *Rt = qp.R + t * qp.r_stride;
+        double h;
+        if (POLISH) {
+            // h_F = R_FF ub_F - R_F,fix (b - ub_fix)
+            const int mi = s.mask[e];
+            if (mi) {
+                h = mi == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i);
+            } else {
+                h = 0.0;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const int mk = s.mask[t * M + j];
+                    const double ubj = qp.ub[t * M + j];
+                    h += mk ? -Rt[i * M + j] * ((mk == 1 ? box_lo(s, qp.sat, t, j) : box_hi(s, qp.sat, t, j)) - ubj)
+                            : Rt[i * M + j] * ubj;
+                }
+            }
+        } else {
+            h = qp.Rub[e] + rho_half * (s.z[e] - s.y[e]);
+        }
+        s.hl[e] = h;
+    }
     double p = act ? -qp.qlinf[lane] : 0.0;
     double dv_n = act ? ws_rec<CF>(sr, H - 1)[R_::DV + lane] : 0.0;
     double ql_n = act ? qp.qlin[(H - 1) * N + lane] : 0.0;
+#pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double *slot = s.ring + (t & 1) * R_::SIZE;
-        const double *Bt = slot + R_::B;
         double *vec = (t & 1) ? s.vb : s.va;
         const double v = dv_n + p, ql = ql_n;
         if (act) vec[lane] = v;
@@ -574,59 +604,31 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
         if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), 0, R_::SIZE, lane);
         double g[M];
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * v : 0.0;
+        for (int i = 0; i < M; ++i) g[i] = act ? slot[R_::B + lane * M + i] * v : 0.0;
         warp_sum_vec<M>(g, lane);
         const double atv = cmatvec<CF, true>(ops, phi_t, t, vec, lane);
-        const double *Rt = qp.R + t * qp.r_stride;
 #pragma unroll
-        for (int i = 0; i < M; ++i) {
-            double h;
-            if (POLISH) {
-                // h_F = R_FF ub_F - R_F,fix (b - ub_fix); pinned controls come out as 0 and are overwritten by b
-                if (s.mask[t * M + i]) {
-                    g[i] = 0.0;
-                    continue;
-                }
-                h = 0.0;
+        for (int i = 0; i < M; ++i) g[i] = s.mask[t * M + i] ? 0.0 : g[i] - s.hl[t * M + i];
+        if (lane < M) {
+            double kkv = 0.0;
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    const int mk = s.mask[t * M + j];
-                    const double ubj = qp.ub[t * M + j];
-                    h += mk ? -Rt[i * M + j] * ((mk == 1 ? box_lo(s, qp.sat, t, j) : box_hi(s, qp.sat, t, j)) - ubj)
-                            : Rt[i * M + j] * ubj;
-                }
-            } else {
-                h = qp.Rub[t * M + i] + rho_half * (s.z[t * M + i] - s.y[t * M + i]);
-            }
-            g[i] -= h;
+            for (int b = 0; b < M; ++b) kkv = fma(slot[R_::SINV + lane * M + b], g[b], kkv);
+            s.kk[t * M + lane] = kkv;
         }
-        double kkv[M];
+        double pn = atv - ql;
 #pragma unroll
-        for (int a = 0; a < M; ++a) {
-            kkv[a] = 0.0;
-#pragma unroll
-            for (int b = 0; b < M; ++b) kkv[a] = fma(slot[R_::SINV + a * M + b], g[b], kkv[a]);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int a = 0; a < M; ++a) s.kk[t * M + a] = kkv[a];
-        }
-        if (act) {
-            double pn = atv - ql;
-#pragma unroll
-            for (int a = 0; a < M; ++a) pn = fma(-slot[R_::K + a * N + lane], g[a], pn);
-            p = pn;
-        }
+        for (int a = 0; a < M; ++a) pn = fma(act ? -slot[R_::K + a * N + lane] : 0.0, g[a], pn);
+        p = pn;
     }
     __syncwarp();   // kk complete; va/vb free again
     // forward: record 0 is still in slot 0
     double *Xo = ws_Xo<CF>(sr);
     double x = act ? s.x0[lane] : 0.0;
     if (WRITE_X && act) Xo[lane] = x;
+#pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double *slot = s.ring + (t & 1) * R_::SIZE;
-        const double *Bt = slot + R_::B;
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) vec[lane] = x;
         cp_async_wait_all();
@@ -638,21 +640,17 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
         warp_sum_vec<M>(u, lane);
         const double ax = cmatvec<CF, false>(ops, phi_t, t, vec, lane);
 #pragma unroll
-        for (int a = 0; a < M; ++a) {
-            u[a] = -u[a] - s.kk[t * M + a];
-            if (POLISH) {
-                const int mk = s.mask[t * M + a];
-                if (mk) u[a] = mk == 1 ? box_lo(s, qp.sat, t, a) : box_hi(s, qp.sat, t, a);
-            }
-        }
-        if (lane == 0) {
+        for (int a = 0; a < M; ++a) u[a] = s.mask[t * M + a] ? s.hl[t * M + a] : -u[a] - s.kk[t * M + a];
+        if (lane < M) {
+            double uv = u[0];
 #pragma unroll
-            for (int a = 0; a < M; ++a) s.Uo[t * M + a] = u[a];
+            for (int a = 1; a < M; ++a) uv = (lane == a) ? u[a] : uv;
+            s.Uo[t * M + lane] = uv;
         }
         if (act) {
             double xn = ax + slot[R_::D + lane];
 #pragma unroll
-            for (int a = 0; a < M; ++a) xn = fma(Bt[lane * M + a], u[a], xn);
+            for (int a = 0; a < M; ++a) xn = fma(slot[R_::B + lane * M + a], u[a], xn);
             x = xn;
             if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
@@ -768,6 +766,8 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     bool run_admm = !set.polish || set.admm_first;
     for (;;) {
         if (run_admm) {
+            for (int e = lane; e < HM; e += 32) s.mask[e] = 0;   // the sweeps read the working set: none in ADMM
+            __syncwarp();
             riccati_factor<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, lane);
             cnt.factor++;
             for (int it = 0; it < set.max_admm; ++it) {
@@ -976,6 +976,7 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
 #pragma unroll
             for (int i = 0; i < M; ++i) b[i] = 0.0;
             const double2 *blk = model.blocks + (C + r) * C;
+#pragma unroll 1
             for (int kb = 1; kb <= p; ++kb, blk += C * C) {
                 double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
