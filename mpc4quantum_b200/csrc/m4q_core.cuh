@@ -51,7 +51,7 @@ template <int C_, int M_> struct Cfg {
 //     trajectories and a few vectors -- 13 KB for the transmon, (almost) independent of the horizon, so that
 //     ~16 members are resident per SM;
 //   * L2-resident workspace in global memory (one per resident warp, re-used member after member): the
-//     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t], then the state trajectories
+//     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t | A_t], then the state trajectories
 //     Xg, Xo [(H+1) N].  Records are written with plain stores where they are produced (factor: K, S^-1, dv;
 //     linearisation: B, D) and streamed back one stage ahead of their use through the ring with cp.async
 //     (LDGSTS, 16-byte chunks), so the sweeps never wait on L2.
@@ -62,8 +62,12 @@ template <class CF> struct Rec {
     static constexpr int DV = SINV + rup(CF::M * CF::M, 2);      // [N]
     static constexpr int B = DV + CF::N;                         // [N][M]
     static constexpr int D = B + rup(CF::N * CF::M, 2);          // [N]
-    static constexpr int SIZE = D + CF::N;
-    static_assert(B % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
+    static constexpr int SMALL = D + CF::N;                      // everything but A_t: lives in the slab ring
+    static constexpr int AT = SMALL;                             // [C][C] complex: A_t = sum_k phi_k(u_t) block_k
+    static constexpr int SIZE = AT + 2 * CF::C * CF::C;
+    static_assert(B % 2 == 0 && SMALL % 2 == 0, "records are moved in 16-byte chunks");
+    // during the sweeps the A_t halves of the two ring slots alias the G buffer (only live inside the factor)
+    static_assert(4 * CF::C * CF::C <= CF::KP * CF::LDG, "A_t ring does not fit the G buffer");
 };
 template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
     return H * Rec<CF>::SIZE + 2 * (H + 1) * CF::N;
@@ -97,7 +101,7 @@ template <class CF> struct Slab {
         q->scr = q->W;
         take(&q->T21, M * N);
         take(&q->S, M * M);
-        take(&q->ring, 2 * Rec<CF>::SIZE);
+        take(&q->ring, 2 * Rec<CF>::SMALL);
         take(&q->kk, H * M);
         take(&q->hl, H * M);
         take(&q->phi, H * nblk);
@@ -157,6 +161,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // stream doubles [first, first + count) of a record into a ring slot (first, count even); one group per call
 __device__ __forceinline__ void prefetch_rec(double *slot, const double *rec, int first, int count, int lane) {
+#pragma unroll 1
     for (int c = lane; c < (count >> 1); c += 32) cp_async16(slot + first + 2 * c, rec + first + 2 * c);
     cp_async_commit();
 }
@@ -279,53 +284,43 @@ template <int M> __device__ __forceinline__ void spd_inverse(double (&a)[M][M], 
 
 // ---------------------------------------------------------------------------------------------------------
 // y[lane] = (A_t x)[lane] (TRANS = false) or (A_t^T x)[lane] (TRANS = true) for lane < N; x realified
-// [Re | Im] in shared memory.  A_t = sum_k phi_k blk_k is never formed: with m = blk_k[r][j] (or [j][r]),
+// [Re | Im] in shared memory, A_t complex [C][C].  With m = A_t[r][j] (or [j][r]),
 //   A,   re row:  sum m.x xr - m.y xi      A,   im row:  sum m.x xi + m.y xr
 //   A^T, re row:  sum m.x xr + m.y xi      A^T, im row:  sum m.x xi - m.y xr
 // so each lane reads x through two lane-dependent base pointers and one sign: no selects in the loop.
-// The vector is cached in registers across the blocks; four accumulator chains per block.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool TRANS>
-__device__ __forceinline__ double cmatvec(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
+__device__ __forceinline__ double cmatvec(const double2 *At, const double *x, int lane) {
     constexpr int C = CF::C, N = CF::N;
     if (lane >= N) return 0.0;
     const bool im = lane >= C;
     const int r = im ? lane - C : lane;
     const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
     const double sgn = (im != TRANS) ? 1.0 : -1.0;
-    double pv[C], qv[C];
+    const double2 *blk = At + (TRANS ? r : r * C);
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-        pv[j] = xp[j];
-        qv[j] = xq[j];
-    }
-    const double2 *blk = ops.blocks + (size_t)t * ops.stage_stride + (TRANS ? r : r * C);
-    double out = 0.0;
-#pragma unroll 1
-    for (int kb = 0; kb < ops.nblk; ++kb, blk += C * C) {
-        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const double2 m = blk[TRANS ? j * C : j];
-            if (j & 1) {
-                p1 = fma(m.x, pv[j], p1);
-                q1 = fma(m.y, qv[j], q1);
-            } else {
-                p0 = fma(m.x, pv[j], p0);
-                q0 = fma(m.y, qv[j], q0);
-            }
+        const double2 m = blk[TRANS ? j * C : j];
+        if (j & 1) {
+            p1 = fma(m.x, xp[j], p1);
+            q1 = fma(m.y, xq[j], q1);
+        } else {
+            p0 = fma(m.x, xp[j], p0);
+            q0 = fma(m.y, xq[j], q0);
         }
-        out = fma(phi_t[kb], fma(sgn, q0 + q1, p0 + p1), out);
     }
-    return out;
+    return fma(sgn, q0 + q1, p0 + p1);
 }
+// same product straight from the model blocks, A_t = sum_k phi_k block_k (cold paths: one call per MPC step)
 template <class CF>
 __device__ __forceinline__ double apply_A(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
-    return cmatvec<CF, false>(ops, phi_t, t, x, lane);
-}
-template <class CF>
-__device__ __forceinline__ double apply_AT(const StageOps &ops, const double *phi_t, int t, const double *v, int lane) {
-    return cmatvec<CF, true>(ops, phi_t, t, v, lane);
+    constexpr int C = CF::C;
+    double out = 0.0;
+#pragma unroll 1
+    for (int kb = 0; kb < ops.nblk; ++kb)
+        out = fma(phi_t[kb], cmatvec<CF, false>(ops.blocks + (size_t)t * ops.stage_stride + kb * C * C, x, lane), out);
+    return out;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -360,20 +355,23 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     const int H = sr.H;
     const int g8 = lane >> 2, c4 = lane & 3;   // fragment coordinates of this lane
     // P <- Qf with zero padding; G, W padding rows / columns zeroed once (never written afterwards)
+#pragma unroll 1
     for (int e = lane; e < NP * LDP; e += 32) {
         const int i = e / LDP, j = e % LDP;
         s.P[e] = (i < N && j < N) ? qp.Qf[i * N + j] : 0.0;
     }
+#pragma unroll 1
     for (int e = lane; e < KP * LDG; e += 32) s.AB[e] = 0.0;
-    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), R_::B, R_::SIZE - R_::B, lane);
+    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SMALL, ws_rec<CF>(sr, H - 1), R_::B, R_::SMALL - R_::B, lane);
+#pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
-        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        const double *slot = s.ring + (t & 1) * R_::SMALL;
         double *rec = ws_rec<CF>(sr, t);
         cp_async_wait_all();
         __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
-        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), R_::B, R_::SIZE - R_::B, lane);
+        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SMALL, ws_rec<CF>(sr, t - 1), R_::B, R_::SMALL - R_::B, lane);
         // realified A_t into G[:, 0:N]
 #pragma unroll 1
         for (int e = lane; e < C * C; e += 32) {
@@ -389,9 +387,11 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
             s.AB[r * LDG + C + j] = -ai;
             s.AB[(C + r) * LDG + j] = ai;
             s.AB[(C + r) * LDG + C + j] = ar;
+            reinterpret_cast<double2 *>(rec + R_::AT)[e] = make_double2(ar, ai);   // for the vector sweeps
         }
         // B~ into G[:, N:Q] and D~ into va
         const double *Bt = slot + R_::B;
+#pragma unroll 1
         for (int e = lane; e < N * M; e += 32) {
             const int k = e / M, i = e % M;
             const bool fixed = masked && s.mask[t * M + i] != 0;
@@ -542,31 +542,59 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     __syncwarp();
 }
 
+// stream stage record t into its ring slot: doubles [first, SMALL) into the slab ring, A_t into the G buffer
+template <class CF>
+__device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int first, int lane) {
+    using R_ = Rec<CF>;
+    const double *rec = ws_rec<CF>(sr, t);
+    double *sm = s.ring + (t & 1) * R_::SMALL;
+#pragma unroll 1
+    for (int c = lane; c < ((R_::SMALL - first) >> 1); c += 32) cp_async16(sm + first + 2 * c, rec + first + 2 * c);
+    double *at = s.AB + (t & 1) * (2 * CF::C * CF::C);
+#pragma unroll 1
+    for (int c = lane; c < CF::C * CF::C; c += 32) cp_async16(at + 2 * c, rec + R_::AT + 2 * c);
+    cp_async_commit();
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// Vector sweeps: backward (costate) then forward (rollout).  Writes Uo and, if WRITE_X, Xo (workspace).
-// POLISH: controls with mask != 0 are pinned to their bound; otherwise the ADMM linear term (mask must be 0).
-// A pre-pass folds both cases into one array hl: the linear term h of a free control, the bound of a pinned one.
-// Stage records arrive through the ring one stage ahead; the two per-lane scalars needed before the stage's only
-// warp sync (dv_t, qlin_t) are register-prefetched.
+// Vector sweeps.  One routine, three modes (one copy of the code in the instruction cache):
+//   SWEEP_ADMM    backward costate + forward rollout of the ADMM u-update (mask must be all zero)
+//   SWEEP_POLISH  the same with the controls of the working set (mask != 0) pinned to their bound
+//   SWEEP_ADJOINT backward only: adjoint gradient of the condensed cost at (Xo, Uo) -> kk, returns max |grad|
+//                 lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};
+//                 lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}          (diagonal costs; else adjoint_gradient())
+// All three are the recursion  v = dv + p;  g = B^T v - h;  p <- A^T v - q - K^T g  with different (dv, h, q, K).
+// A pre-pass folds the control-space terms into one array hl: the linear term h of a free control, the bound of a
+// pinned one.  Stage records arrive through the ring one stage ahead; the per-lane scalars needed before the
+// stage's only warp sync are register-prefetched.  Writes Uo and, if WRITE_X, Xo (workspace).
 // ---------------------------------------------------------------------------------------------------------
+enum { SWEEP_ADMM = 0, SWEEP_POLISH = 1, SWEEP_ADJOINT = 2 };
+
 template <class CF, bool FUSED>
-__device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
-                                           bool POLISH, bool WRITE_X, int lane) {
-    constexpr int N = CF::N, M = CF::M;
+__device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, double rho_half, int mode, bool WRITE_X,
+                                             int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
     using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
-    const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const bool act = lane < N;
-    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), 0, R_::SIZE, lane);
+    const bool adj = mode == SWEEP_ADJOINT;
+    double *Xo = ws_Xo<CF>(sr);
+    prefetch_stage<CF>(s, sr, H - 1, 0, lane);
 #pragma unroll 1
     for (int e = lane; e < H * M; e += 32) {
         const int t = e / M, i = e % M;
         const double *Rt = qp.R + t * qp.r_stride;
         double h;
-        if (POLISH) {
-            // h_F = R_FF ub_F - R_F,fix (b - ub_fix)
+        if (mode == SWEEP_ADMM) {
+            h = qp.Rub[e] + rho_half * (s.z[e] - s.y[e]);
+        } else if (adj) {
+            h = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) h = fma(-2.0 * Rt[i * M + j], s.Uo[t * M + j] - qp.ub[t * M + j], h);
+        } else {
+            // h_F = R_FF ub_F - R_F,fix (b - ub_fix); a pinned control gets its bound
             const int mi = s.mask[e];
             if (mi) {
                 h = mi == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i);
@@ -580,65 +608,76 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
                             : Rt[i * M + j] * ubj;
                 }
             }
-        } else {
-            h = qp.Rub[e] + rho_half * (s.z[e] - s.y[e]);
         }
         s.hl[e] = h;
     }
-    double p = act ? -qp.qlinf[lane] : 0.0;
-    double dv_n = act ? ws_rec<CF>(sr, H - 1)[R_::DV + lane] : 0.0;
-    double ql_n = act ? qp.qlin[(H - 1) * N + lane] : 0.0;
+    // q_t per lane: Qbar_t r_t (table) for the Riccati modes, -2 Qbar_t (x_t - r_t) for the adjoint (diagonal Qbar)
+    auto q_of = [&](int t) -> double {
+        if (!adj) return qp.qlin[t * N + lane];
+        return -2.0 * qp.Q[t * qp.q_stride + lane * N + lane] * (Xo[t * N + lane] - qp.r[t * N + lane]);
+    };
+    double p = 0.0, dv_n = 0.0, ql_n = 0.0, gmax = 0.0;
+    if (act) {
+        p = adj ? 2.0 * qp.Qf[lane * N + lane] * (Xo[H * N + lane] - qp.r[H * N + lane]) : -qp.qlinf[lane];
+        if (!adj) dv_n = ws_rec<CF>(sr, H - 1)[R_::DV + lane];
+        ql_n = q_of(H - 1);
+    }
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *phi_t = s.phi + t * ops.nblk;
-        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        const double *slot = s.ring + (t & 1) * R_::SMALL;
+        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
         double *vec = (t & 1) ? s.vb : s.va;
         const double v = dv_n + p, ql = ql_n;
         if (act) vec[lane] = v;
         if (t > 0 && act) {
-            dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
-            ql_n = qp.qlin[(t - 1) * N + lane];
+            if (!adj) dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
+            ql_n = q_of(t - 1);
         }
         cp_async_wait_all();
         __syncwarp();
-        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), 0, R_::SIZE, lane);
+        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, 0, lane);
         double g[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) g[i] = act ? slot[R_::B + lane * M + i] * v : 0.0;
         warp_sum_vec<M>(g, lane);
-        const double atv = cmatvec<CF, true>(ops, phi_t, t, vec, lane);
+        const double atv = cmatvec<CF, true>(At, vec, lane);
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = s.mask[t * M + i] ? 0.0 : g[i] - s.hl[t * M + i];
+        for (int i = 0; i < M; ++i) {
+            g[i] = (!adj && s.mask[t * M + i]) ? 0.0 : g[i] - s.hl[t * M + i];
+            gmax = fmax(gmax, fabs(g[i]));
+        }
+        double pn = atv - ql;
         if (lane < M) {
             double kkv = 0.0;
 #pragma unroll
-            for (int b = 0; b < M; ++b) kkv = fma(slot[R_::SINV + lane * M + b], g[b], kkv);
+            for (int b = 0; b < M; ++b) kkv = fma(adj ? (b == lane ? 1.0 : 0.0) : slot[R_::SINV + lane * M + b], g[b], kkv);
             s.kk[t * M + lane] = kkv;
         }
-        double pn = atv - ql;
+        if (!adj) {
 #pragma unroll
-        for (int a = 0; a < M; ++a) pn = fma(act ? -slot[R_::K + a * N + lane] : 0.0, g[a], pn);
+            for (int a = 0; a < M; ++a) pn = fma(act ? -slot[R_::K + a * N + lane] : 0.0, g[a], pn);
+        }
         p = pn;
     }
     __syncwarp();   // kk complete; va/vb free again
+    if (adj) return gmax;
     // forward: record 0 is still in slot 0
-    double *Xo = ws_Xo<CF>(sr);
     double x = act ? s.x0[lane] : 0.0;
     if (WRITE_X && act) Xo[lane] = x;
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
-        const double *phi_t = s.phi + t * ops.nblk;
-        const double *slot = s.ring + (t & 1) * R_::SIZE;
+        const double *slot = s.ring + (t & 1) * R_::SMALL;
+        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) vec[lane] = x;
         cp_async_wait_all();
         __syncwarp();
-        if (t + 1 < H) prefetch_rec(s.ring + ((t + 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t + 1), 0, R_::SIZE, lane);
+        if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, 0, lane);
         double u[M];
 #pragma unroll
         for (int a = 0; a < M; ++a) u[a] = act ? slot[R_::K + a * N + lane] * x : 0.0;
         warp_sum_vec<M>(u, lane);
-        const double ax = cmatvec<CF, false>(ops, phi_t, t, vec, lane);
+        const double ax = cmatvec<CF, false>(At, vec, lane);
 #pragma unroll
         for (int a = 0; a < M; ++a) u[a] = s.mask[t * M + a] ? s.hl[t * M + a] : -u[a] - s.kk[t * M + a];
         if (lane < M) {
@@ -656,6 +695,7 @@ __device__ __noinline__ void riccati_solve(SlabRef sr, const StageOps &ops_in, c
         }
     }
     __syncwarp();
+    return 0.0;
 }
 
 // (Qbar v)[lane] for v in shared memory
@@ -676,28 +716,29 @@ __device__ __forceinline__ double apply_Q(const double *Qm, int q_diag, const do
 // ---------------------------------------------------------------------------------------------------------
 // Adjoint gradient of the condensed cost at (Xo, Uo) -> s.kk[t*M+i] (re-used as scratch); returns max |grad|.
 //   lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};  lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}
-// B_t through the ring, x_t - r_t register-prefetched; vectors double-buffered (va/vb, and W as scratch).
+// General (non-diagonal cost) version; the diagonal case runs as a mode of riccati_solve.
+// B_t, A_t through the ring, x_t - r_t register-prefetched; vectors double-buffered (va/vb, and W as scratch).
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
-__device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, int lane) {
-    constexpr int N = CF::N, M = CF::M;
+__device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
     using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
-    const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const bool act = lane < N;
     const double *Xo = ws_Xo<CF>(sr);
-    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, H - 1), R_::B, R_::SIZE - R_::B, lane);
+    prefetch_stage<CF>(s, sr, H - 1, R_::B, lane);
     double xd_n = act ? Xo[(H - 1) * N + lane] - qp.r[(H - 1) * N + lane] : 0.0;
     if (act) s.W[lane] = Xo[H * N + lane] - qp.r[H * N + lane];
     __syncwarp();
     double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.W, lane);
     double gmax = 0.0;
     __syncwarp();
+#pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *phi_t = s.phi + t * ops.nblk;
-        const double *Bt = s.ring + (t & 1) * R_::SIZE + R_::B;
+        const double *Bt = s.ring + (t & 1) * R_::SMALL + R_::B;
+        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
         const double *Rt = qp.R + t * qp.r_stride;
         double *lamv = (t & 1) ? s.vb : s.va;
         double *xdv = s.W + (t & 1) * N;
@@ -709,7 +750,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_
         }
         cp_async_wait_all();
         __syncwarp();
-        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SIZE, ws_rec<CF>(sr, t - 1), R_::B, R_::SIZE - R_::B, lane);
+        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, R_::B, lane);
         double g[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * lam : 0.0;
@@ -724,7 +765,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const StageOps &ops_
 #pragma unroll
             for (int i = 0; i < M; ++i) s.kk[t * M + i] = g[i];
         }
-        const double atl = cmatvec<CF, true>(ops, phi_t, t, lamv, lane);
+        const double atl = cmatvec<CF, true>(At, lamv, lane);
         lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, xdv, lane);
     }
     __syncwarp();
@@ -755,6 +796,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     const int HM = H * M;
     const double rho_half = 0.5 * set.rho;
     // clip the warm start into the current box
+#pragma unroll 1
     for (int e = lane; e < HM; e += 32) {
         const int t = e / M, i = e % M;
         s.z[e] = fmin(fmax(s.z[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
@@ -766,14 +808,16 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     bool run_admm = !set.polish || set.admm_first;
     for (;;) {
         if (run_admm) {
+#pragma unroll 1
             for (int e = lane; e < HM; e += 32) s.mask[e] = 0;   // the sweeps read the working set: none in ADMM
             __syncwarp();
             riccati_factor<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, lane);
             cnt.factor++;
             for (int it = 0; it < set.max_admm; ++it) {
-                riccati_solve<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, !set.polish, lane);
+                riccati_solve<CF, FUSED>(sr, qp_in, rho_half, SWEEP_ADMM, !set.polish, lane);
                 cnt.admm++;
                 bool bad = false;
+#pragma unroll 1
                 for (int e = lane; e < HM; e += 32) {
                     const int t = e / M, i = e % M;
                     const double u = s.Uo[e], zo = s.z[e];
@@ -789,11 +833,13 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         }
         if (!set.polish) {
             // OSQP-equivalent mode: report the feasible iterate z and its rollout
+#pragma unroll 1
             for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
             __syncwarp();
             double *Xo = ws_Xo<CF>(sr);
             double x = (lane < N) ? s.x0[lane] : 0.0;
             if (lane < N) Xo[lane] = x;
+#pragma unroll 1
             for (int t = 0; t < H; ++t) {
                 const double *rec = ws_rec<CF>(sr, t);
                 if (lane < N) s.va[lane] = x;
@@ -811,6 +857,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             break;
         }
         // ---- working set from the (z, y) estimate: at a bound with the multiplier pushing outwards
+#pragma unroll 1
         for (int e = lane; e < HM; e += 32) {
             const int t = e / M, i = e % M;
             const double zz = s.z[e], yy = s.y[e];
@@ -825,10 +872,12 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             riccati_factor<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
             cnt.factor++;
             cnt.polish++;
-            riccati_solve<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, true, lane);
-            const double gmax = adjoint_gradient<CF, FUSED>(sr, ops_in, qp_in, lane);
+            riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_POLISH, true, lane);
+            const double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
+                                           : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             const double gs = fmax(1.0, gmax);
             bool changed = false;
+#pragma unroll 1
             for (int e = lane; e < HM; e += 32) {
                 const int t = e / M, i = e % M;
                 const int mk = s.mask[e];
@@ -857,6 +906,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         if (certified) {
             // warm start of the next solve: z = u*, y = the (scaled) multipliers of the pinned controls
             const double inv_rho = 1.0 / set.rho;
+#pragma unroll 1
             for (int e = lane; e < HM; e += 32) {
                 const int t = e / M, i = e % M;
                 s.z[e] = fmin(fmax(s.Uo[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
@@ -870,6 +920,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         run_admm = true;
         if (eps < 1e-10) {
             status = 2;   // could not certify: report the ADMM iterate (reference: solver warning -> exit code 2)
+#pragma unroll 1
             for (int e = lane; e < HM; e += 32) s.Uo[e] = s.z[e];
             __syncwarp();
             break;
@@ -877,9 +928,11 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     }
     // non-finite result -> reference exit code 3 (mpc.py:200-203)
     bool nonfinite = false;
+#pragma unroll 1
     for (int e = lane; e < HM; e += 32) nonfinite |= !isfinite(s.Uo[e]);
     {
         const double *Xo = ws_Xo<CF>(sr);
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N; e += 32) nonfinite |= !isfinite(Xo[e]);
     }
     if (__any_sync(FULL, nonfinite)) status = 3;
@@ -894,6 +947,7 @@ __device__ double qp_objective(const SlabRef &sr, const QPData &qp, int lane) {
     const int H = sr.H;
     const double *Xo = ws_Xo<CF>(sr);
     double acc = 0.0;
+#pragma unroll 1
     for (int t = 0; t <= H; ++t) {
         __syncwarp();
         if (lane < N) s.vb[lane] = Xo[t * N + lane] - qp.r[t * N + lane];
@@ -901,6 +955,7 @@ __device__ double qp_objective(const SlabRef &sr, const QPData &qp, int lane) {
         const double qv = apply_Q<CF>(t == H ? qp.Qf : qp.Q + t * qp.q_stride, qp.q_diag, s.vb, lane);
         if (lane < N) acc = fma(qv, s.vb[lane], acc);
     }
+#pragma unroll 1
     for (int e = lane; e < H * M; e += 32) {
         const int t = e / M, i = e % M;
         const double *Rt = qp.R + t * qp.r_stride;
@@ -932,6 +987,7 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
     const int r = im ? lane - C : lane;
     const double sgn = im ? 1.0 : -1.0;
     double x_n = act ? Xg[lane] : 0.0;
+#pragma unroll 1
     for (int t = 0; t < H; ++t) {
         double *dco = s.scr + (t & 1) * (p * M);   // [p][M]
         double *vec = (t & 1) ? s.vb : s.va;
@@ -950,6 +1006,7 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
                 const int e = pow[lane * M + l];
                 const double ul = s.Ug[t * M + l];
                 double pw = 1.0, pwm1 = 1.0;   // u^e and u^(e-1)
+#pragma unroll 1
                 for (int q = 0; q < e; ++q) {
                     pwm1 = pw;
                     pw *= ul;
@@ -1041,6 +1098,7 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
             den = fma(qd * d_k, d_k, den);
         }
     } else {
+#pragma unroll 1
         for (int tau = 0; tau <= H; ++tau) {
             double e_k = 0.0, d_k = 0.0;
             if (lane < N) {
@@ -1074,6 +1132,7 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
     }
     // control part: Z_U = [U.ravel() (index i*H + t), zeros(mH)], blocks tau < H of size 2M: [[R,0],[0,R]]
     const int HM = H * M;
+#pragma unroll 1
     for (int tau = 0; tau < H; ++tau) {
         const double *Rt = qp.R + tau * qp.r_stride;
         if (lane < 2 * M) {
@@ -1086,6 +1145,7 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
                 da = s.Uo[t * M + i] - s.Ug[t * M + i];
             }
             double re = 0.0, rd = 0.0;
+#pragma unroll 1
             for (int jb = 0; jb < M; ++jb) {
                 const int zb = tau * 2 * M + blk_row * M + jb;
                 if (zb < HM) {
@@ -1099,6 +1159,7 @@ __device__ __noinline__ void line_search(SlabRef sr, const QPData &qp_in, int la
             den = fma(rd, da, den);
         }
     }
+#pragma unroll 1
     for (int e = lane; e < HM; e += 32) {
         const double d = s.Uo[e] - s.Ug[e];
         nrm = fma(d, d, nrm);
@@ -1129,6 +1190,7 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
 // out(i,j) = sum_k A[i][k] B[k][j] (lane holds out entry); A, B in shared memory as double2 [d*d]
 __device__ __forceinline__ double2 cmm(const double2 *A, const double2 *B, int d, int i, int j) {
     double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 1
     for (int k = 0; k < d; ++k) acc = cfma(A[i * d + k], B[k * d + j], acc);
     return acc;
 }
@@ -1152,6 +1214,7 @@ __device__ __noinline__ void expm_minus_i(const double2 *Hm, double dt, int d, d
     double nrm = 0.0;
     if (act) {
         double cs = 0.0;
+#pragma unroll 1
         for (int k = 0; k < d; ++k) cs += T1[k * d + j].x;
         nrm = cs;
     }
@@ -1183,6 +1246,7 @@ __device__ __noinline__ void expm_minus_i(const double2 *Hm, double dt, int d, d
         if (act) T0[lane] = v;
         __syncwarp();
     }
+#pragma unroll 1
     for (int q = 0; q < sq; ++q) {
         double2 v = make_double2(0.0, 0.0);
         if (act) v = cmm(T0, T0, d, i, j);
@@ -1201,6 +1265,7 @@ __device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, do
     __syncwarp();
     double2 v = make_double2(0.0, 0.0);
     if (act) {
+#pragma unroll 1
         for (int k = 0; k < d; ++k) {
             const double2 uc = U[j * d + k];
             v = cfma(tmp[i * d + k], make_double2(uc.x, -uc.y), v);

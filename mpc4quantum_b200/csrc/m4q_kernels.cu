@@ -74,16 +74,19 @@ __global__ void build_tables(int C, int M, int n_targ, const double2 *Q, const d
         tab[L.Qfr + e] = realified_sym(Qf, C, e / N, e % N);
     }
     for (int e = tid; e < M * M; e += nt) tab[L.Rr + e] = 0.5 * (R[e] + R[(e % M) * M + e / M]);
+#pragma unroll 1
     for (int e = tid; e < n_targ * N; e += nt) {
         const int col = e / N, k = e % N;
         const double2 v = X_targ[(k % C) * n_targ + col];
         tab[L.r + e] = k < C ? v.x : v.y;
     }
+#pragma unroll 1
     for (int e = tid; e < n_targ * M; e += nt) {
         const int col = e / M, i = e % M;
         tab[L.ub + e] = col < n_targ - 1 ? U_targ[i * (n_targ - 1) + col] : 0.0;
     }
     __syncthreads();
+#pragma unroll 1
     for (int e = tid; e < n_targ * N; e += nt) {
         const int col = e / N, k = e % N;
         double a = 0.0, b = 0.0;
@@ -95,6 +98,7 @@ __global__ void build_tables(int C, int M, int n_targ, const double2 *Q, const d
         tab[L.qlin + e] = a;
         tab[L.qlinf + e] = b;
     }
+#pragma unroll 1
     for (int e = tid; e < n_targ * M; e += nt) {
         const int col = e / M, i = e % M;
         double a = 0.0;
@@ -132,6 +136,7 @@ __device__ void lift_state(int mode, int d, const double2 *rho, double *out, int
         if (lane < 2 * half) {
             const int which = lane / half, e = lane % half, a = e / dA, b = e % dA;
             double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 1
             for (int k = 0; k < dA; ++k) {
                 // which = 0: rhoA[a][b] = sum_k rho[(a,k),(b,k)];  which = 1: rhoB[a][b] = sum_k rho[(k,a),(k,b)]
                 const int row = which == 0 ? a * dA + k : k * dA + a;
@@ -220,12 +225,14 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     double *Qfr = Qr + N * N;
     double *Rr = Qfr + N * N;
     int *pow = reinterpret_cast<int *>(Rr + rup(M * M, 2));
+#pragma unroll 1
     for (int e = threadIdx.x; e < a.nblk * C * C; e += blockDim.x) blocks[e] = a.A_blocks[e];
     for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
         Qr[e] = a.tab[L.Qr + e];
         Qfr[e] = a.tab[L.Qfr + e];
     }
     for (int e = threadIdx.x; e < M * M; e += blockDim.x) Rr[e] = a.tab[L.Rr + e];
+#pragma unroll 1
     for (int e = threadIdx.x; e < (a.nblk - 1) * M; e += blockDim.x) pow[e] = a.powers[e];
     __syncthreads();
 
@@ -272,7 +279,9 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
             }
             __syncwarp();
             lift_state<CF>(a.external_plant ? M4Q_LIFT_IDENTITY : a.lift_mode, d, xcur, s.x0, lane);
+#pragma unroll 1
             for (int e = lane; e < (H + 1) * N; e += 32) Xg[e] = s.x0[e % N];     // mpc.py:141
+#pragma unroll 1
             for (int e = lane; e < H * M; e += 32) {                              // mpc.py:142
                 s.Ug[e] = 0.0;
                 s.z[e] = 0.0;
@@ -281,8 +290,10 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         } else {
             const double *st = a.state + (size_t)k * persist;
             int o = 0;
+#pragma unroll 1
             for (int e = lane; e < (H + 1) * N; e += 32) Xg[e] = st[o + e];
             o += (H + 1) * N;
+#pragma unroll 1
             for (int e = lane; e < H * M; e += 32) {
                 s.Ug[e] = st[o + e];
                 s.z[e] = st[o + H * M + e];
@@ -357,6 +368,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                         const double xg = Xg[e];
                         Xg[e] = fma(alpha, Xo[e] - xg, xg);
                     }
+#pragma unroll 1
                     for (int e = lane; e < H * M; e += 32) s.Ug[e] = fma(alpha, s.Uo[e] - s.Ug[e], s.Ug[e]);
                     __syncwarp();
                     ++n_iter;
@@ -371,6 +383,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                 if (!a.external_plant) {
                     if ((step + 1) % a.mf == 0) {
                         // plant window, newest control first (mpc.py:257): segment j uses us[step - j]
+#pragma unroll 1
                         for (int j = 0; j < a.mf; ++j) {
                             if (lane < dd) {
                                 double2 h = H0k[lane];
@@ -395,6 +408,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                             if (lane > 0)
                                 for (int l = 0; l < M; ++l) {
                                     const double ul = s.Uo[l];
+#pragma unroll 1
                                     for (int q = 0; q < pow[(lane - 1) * M + l]; ++q) phi *= ul;
                                 }
                             s.scr[lane] = phi;
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                     for (int t = 0; t < H; ++t) Xg[t * N + lane] = Xg[(t + 1) * N + lane];
                 }
                 if (lane < M)
+#pragma unroll 1
                     for (int t = 0; t + 1 < H; ++t) {
                         s.Ug[t * M + lane] = s.Ug[(t + 1) * M + lane];
                         s.z[t * M + lane] = s.z[(t + 1) * M + lane];
@@ -465,8 +480,10 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         if (a.state) {
             double *st = a.state + (size_t)k * persist;
             int o = 0;
+#pragma unroll 1
             for (int e = lane; e < (H + 1) * N; e += 32) st[o + e] = Xg[e];
             o += (H + 1) * N;
+#pragma unroll 1
             for (int e = lane; e < H * M; e += 32) {
                 st[o + e] = s.Ug[e];
                 st[o + H * M + e] = s.z[e];
@@ -526,27 +543,33 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         const double2 *Xb = a.X_bm + (size_t)k * C * (H + 1);
         const double *Ub = a.U_bm + (size_t)k * M * H;
         // ---- realify the instance (optimize.py:21-35)
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N * N; e += 32) {
             const int t = e / (N * N), ij = e % (N * N);
             wQ[e] = realified_sym(Qk + (size_t)t * C * C, C, ij / N, ij % N);
         }
+#pragma unroll 1
         for (int e = lane; e < H * M * M; e += 32) {
             const int t = e / (M * M), ij = e % (M * M);
             wR[e] = 0.5 * (Rk[t * M * M + ij] + Rk[t * M * M + (ij % M) * M + ij / M]);
         }
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 v = Xb[(kk % C) * (H + 1) + t];
             wr[e] = kk < C ? v.x : v.y;
         }
+#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) wub[e] = Ub[(e % M) * H + e / M];
         __syncwarp();
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             double acc = 0.0;
             for (int j = 0; j < N; ++j) acc = fma(wQ[(size_t)t * N * N + kk * N + j], wr[t * N + j], acc);
             wql[e] = acc;
         }
+#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) {
             const int t = e / M, i = e % M;
             double acc = 0.0;
@@ -556,17 +579,21 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         // ---- slab: B, D, x0, bounds, cold ADMM start
         const double2 *Bk = a.B_ls + (size_t)k * H * C * M;
         const double2 *Dk = a.D_ls + (size_t)k * H * C;
+#pragma unroll 1
         for (int e = lane; e < H * N * M; e += 32) {
             const int t = e / (N * M), rem = e % (N * M), kk = rem / M, i = rem % M;
             const double2 v = Bk[((size_t)t * C + kk % C) * M + i];
             ws_rec<CF>(sr, t)[Rec<CF>::B + rem] = kk < C ? v.x : v.y;
         }
+#pragma unroll 1
         for (int e = lane; e < H * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 v = Dk[(size_t)t * C + kk % C];
             ws_rec<CF>(sr, t)[Rec<CF>::D + kk] = kk < C ? v.x : v.y;
         }
+#pragma unroll 1
         for (int e = lane; e < H; e += 32) s.phi[e] = 1.0;
+#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) {
             s.z[e] = 0.0;
             s.y[e] = 0.0;
@@ -614,10 +641,12 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         double2 *Xo = a.X_out + (size_t)k * C * (H + 1);
         double *Uo = a.U_out + (size_t)k * M * H;
         const double *wXo = ws_Xo<CF>(sr);
+#pragma unroll 1
         for (int e = lane; e < C * (H + 1); e += 32) {
             const int kk = e / (H + 1), t = e % (H + 1);
             Xo[e] = make_double2(wXo[t * N + kk], wXo[t * N + C + kk]);
         }
+#pragma unroll 1
         for (int e = lane; e < M * H; e += 32) Uo[e] = s.Uo[(e % H) * M + e / H];
         if (lane == 0) {
             a.obj_out[k] = obj;
@@ -665,17 +694,20 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         const double2 *Xk = a.Xg + (size_t)k * C * (H + 1);
         const double *Uk = a.Ug + (size_t)k * M * H;
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 v = Xk[(kk % C) * (H + 1) + t];
             wXg[e] = kk < C ? v.x : v.y;
         }
+#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) s.Ug[e] = Uk[(e % M) * H + e / M];
         __syncwarp();
         linearize<CF, false>(sr, model, a.powers, lane);
         double2 *Ao = a.A_out + (size_t)k * H * C * C;
         double2 *Bo = a.B_out + (size_t)k * H * C * M;
         double2 *Do = a.D_out + (size_t)k * H * C;
+#pragma unroll 1
         for (int e = lane; e < H * C * C; e += 32) {
             const int t = e / (C * C), ij = e % (C * C);
             double2 acc = make_double2(0.0, 0.0);
@@ -687,11 +719,13 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
             }
             Ao[e] = acc;
         }
+#pragma unroll 1
         for (int e = lane; e < H * C * M; e += 32) {
             const int t = e / (C * M), rem = e % (C * M), r = rem / M, i = rem % M;
             const double *rec = ws_rec<CF>(sr, t);
             Bo[e] = make_double2(rec[Rec<CF>::B + r * M + i], rec[Rec<CF>::B + (C + r) * M + i]);
         }
+#pragma unroll 1
         for (int e = lane; e < H * C; e += 32) {
             const int t = e / C, r = e % C;
             const double *rec = ws_rec<CF>(sr, t);
@@ -714,6 +748,7 @@ __global__ void line_search_prep(int C, int M, int H, const double2 *Q_ls, const
         const int t = e / (N * N), ij = e % (N * N);
         wQ[e] = realified_sym(Q_ls + (size_t)t * C * C, C, ij / N, ij % N);
     }
+#pragma unroll 1
     for (int e = tid; e < H * M * M; e += nt) {
         const int t = e / (M * M), ij = e % (M * M);
         wR[e] = 0.5 * (R_ls[t * M * M + ij] + R_ls[t * M * M + (ij % M) * M + ij / M]);
@@ -723,6 +758,7 @@ __global__ void line_search_prep(int C, int M, int H, const double2 *Q_ls, const
         const double2 v = X_ref[(kk % C) * (H + 1) + t];
         wr[e] = kk < C ? v.x : v.y;
     }
+#pragma unroll 1
     for (int e = tid; e < H * M; e += nt) wub[e] = U_ref[(e % M) * H + e / M];
 }
 
@@ -763,12 +799,14 @@ __global__ void __launch_bounds__(CF::MAXW * 32) line_search_kernel(const LsArgs
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         const double2 *Xgk = a.Xg + (size_t)k * C * (H + 1), *Xok = a.Xo + (size_t)k * C * (H + 1);
         const double *Ugk = a.Ug + (size_t)k * M * H, *Uok = a.Uo + (size_t)k * M * H;
+#pragma unroll 1
         for (int e = lane; e < (H + 1) * N; e += 32) {
             const int t = e / N, kk = e % N;
             const double2 g = Xgk[(kk % C) * (H + 1) + t], o = Xok[(kk % C) * (H + 1) + t];
             wXg[e] = kk < C ? g.x : g.y;
             wXo[e] = kk < C ? o.x : o.y;
         }
+#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) {
             s.Ug[e] = Ugk[(e % M) * H + e / M];
             s.Uo[e] = Uok[(e % M) * H + e / M];
@@ -833,11 +871,13 @@ __global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, 
     double2 *cur = smem2, *nxt = cur + (size_t)p1 * cc, *acc = nxt + (size_t)p1 * cc;
     int *succ = reinterpret_cast<int *>(acc + (size_t)p1 * cc);   // succ[e][j]: index of powers[e] + 1_j, or -1
     const int tid = threadIdx.x, nt = blockDim.x;
+#pragma unroll 1
     for (int e = tid; e < p1 * (m + 1); e += nt) {
         const int src = e / (m + 1), j = e % (m + 1);
         int found = -1;
         if (j == 0) found = src;
         else
+#pragma unroll 1
             for (int q = 0; q < p1 && found < 0; ++q) {
                 bool same = true;
                 for (int l = 0; l < m; ++l) same &= powers[q * m + l] == powers[src * m + l] + (l == j - 1 ? 1 : 0);
@@ -849,6 +889,7 @@ __global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, 
     for (long long k = blockIdx.x; k < n; k += gridDim.x) {
         const double2 *Lk = L + (size_t)k * (m + 1) * cc;
         // constant row is the all-zero exponent tuple: find it (row 0 in the reference's ordering)
+#pragma unroll 1
         for (int e = tid; e < p1 * cc; e += nt) {
             const int blk = e / cc, ij = e % cc;
             bool zero = true;
@@ -861,6 +902,7 @@ __global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, 
         double pref = 1.0;
         for (int ord = 1; ord <= order; ++ord) {
             pref *= dt / (double)ord;
+#pragma unroll 1
             for (int e = tid; e < p1 * cc; e += nt) {
                 const int dst = e / cc, ij = e % cc, i = ij / c, jcol = ij % c;
                 double2 sum = make_double2(0.0, 0.0);
@@ -874,6 +916,7 @@ __global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, 
                 nxt[e] = sum;
             }
             __syncthreads();
+#pragma unroll 1
             for (int e = tid; e < p1 * cc; e += nt) {
                 const double2 v = nxt[e];
                 cur[e] = v;
@@ -884,6 +927,7 @@ __global__ void __launch_bounds__(128) taylor_kernel(long long n, int c, int m, 
         }
         // hstack layout: out[i][blk*c + j]
         double2 *ok = out + (size_t)k * c * c * p1;
+#pragma unroll 1
         for (int e = tid; e < p1 * cc; e += nt) {
             const int blk = e / cc, ij = e % cc, i = ij / c, j = ij % c;
             ok[(size_t)i * c * p1 + blk * c + j] = acc[e];
