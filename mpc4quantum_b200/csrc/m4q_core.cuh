@@ -33,6 +33,7 @@ __host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r
 __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };
+template <> struct Tiles<9, 2> { static constexpr int MAXW = 12; };   // 3 warps per scheduler: 168 registers, no spills
 template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
 
 template <int C_, int M_> struct Cfg {
@@ -354,6 +355,25 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const int g8 = lane >> 2, c4 = lane & 3;   // fragment coordinates of this lane
+    // the pairs (i <= j) of the symmetric P update this lane owns, fixed for the whole sweep: packed (i << 8) | j
+    constexpr int NTRI = N * (N + 1) / 2, NPAIR = cdiv(NTRI, 32);
+    int pair[NPAIR];
+    {
+        int i = 0, j = lane;   // element `lane` of the row-major upper triangle, then every 32nd
+        while (i < N && j >= N) {
+            j += i + 1 - N;
+            ++i;
+        }
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+            pair[q] = (i < N) ? ((i << 8) | j) : -1;
+            j += 32;
+            while (i < N && j >= N) {
+                j += i + 1 - N;
+                ++i;
+            }
+        }
+    }
     // P <- Qf with zero padding; G, W padding rows / columns zeroed once (never written afterwards)
 #pragma unroll 1
     for (int e = lane; e < NP * LDP; e += 32) {
@@ -372,22 +392,37 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
         cp_async_wait_all();
         __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
         if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SMALL, ws_rec<CF>(sr, t - 1), R_::B, R_::SMALL - R_::B, lane);
-        // realified A_t into G[:, 0:N]
+        // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
+        {
+            constexpr int NE = cdiv(C * C, 32);
+            double ar[NE], ai[NE];
+#pragma unroll
+            for (int q = 0; q < NE; ++q) ar[q] = ai[q] = 0.0;
+            const double2 *bp = blk0 + lane;
 #pragma unroll 1
-        for (int e = lane; e < C * C; e += 32) {
-            const int r = e / C, j = e % C;
-            double ar = 0.0, ai = 0.0;
-#pragma unroll 1
-            for (int kb = 0; kb < ops.nblk; ++kb) {
-                const double2 v = blk0[kb * C * C + e];
-                ar = fma(phi_t[kb], v.x, ar);
-                ai = fma(phi_t[kb], v.y, ai);
+            for (int kb = 0; kb < ops.nblk; ++kb, bp += C * C) {
+                const double ph = phi_t[kb];
+#pragma unroll
+                for (int q = 0; q < NE; ++q) {
+                    if (lane + 32 * q < C * C) {
+                        const double2 v = bp[32 * q];
+                        ar[q] = fma(ph, v.x, ar[q]);
+                        ai[q] = fma(ph, v.y, ai[q]);
+                    }
+                }
             }
-            s.AB[r * LDG + j] = ar;
-            s.AB[r * LDG + C + j] = -ai;
-            s.AB[(C + r) * LDG + j] = ai;
-            s.AB[(C + r) * LDG + C + j] = ar;
-            reinterpret_cast<double2 *>(rec + R_::AT)[e] = make_double2(ar, ai);   // for the vector sweeps
+#pragma unroll
+            for (int q = 0; q < NE; ++q) {
+                const int e = lane + 32 * q;
+                if (e < C * C) {
+                    const int r = e / C, j = e % C;
+                    s.AB[r * LDG + j] = ar[q];
+                    s.AB[r * LDG + C + j] = -ai[q];
+                    s.AB[(C + r) * LDG + j] = ai[q];
+                    s.AB[(C + r) * LDG + C + j] = ar[q];
+                    reinterpret_cast<double2 *>(rec + R_::AT)[e] = make_double2(ar[q], ai[q]);
+                }
+            }
         }
         // B~ into G[:, N:Q] and D~ into va
         const double *Bt = slot + R_::B;
@@ -519,22 +554,19 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll
                 for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + lane], kv);
                 rec[R_::K + a * N + lane] = kv;
+                s.W[a * N + lane] = kv;   // W is dead after the second product
             }
         }
-        // P_t = Qbar_t + T11 - T21^T S^-1 T21, in place on the upper triangle and mirrored
+        __syncwarp();
+        // P_t = Qbar_t + T11 - T21^T K, in place on the upper triangle and mirrored
         const double *Qt = qp.Q + t * qp.q_stride;
-#pragma unroll 1
-        for (int e = lane; e < N * N; e += 32) {
-            const int i = e / N, j = e % N;
-            if (i > j) continue;
-            double v = s.P[i * LDP + j] + Qt[e];
 #pragma unroll
-            for (int a = 0; a < M; ++a) {
-                double kv = 0.0;
+        for (int q = 0; q < NPAIR; ++q) {
+            if (pair[q] < 0) continue;
+            const int i = pair[q] >> 8, j = pair[q] & 255;
+            double v = s.P[i * LDP + j] + Qt[i * N + j];
 #pragma unroll
-                for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + j], kv);
-                v = fma(-s.T21[a * N + i], kv, v);
-            }
+            for (int a = 0; a < M; ++a) v = fma(-s.T21[a * N + i], s.W[a * N + j], v);
             s.P[i * LDP + j] = v;
             s.P[j * LDP + i] = v;
         }
