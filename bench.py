@@ -29,9 +29,10 @@ UNIT = 'trajectories/s'
 # ----------------------------------------------------------------------------------------------------------
 def workload(name, discretize=None):
     from mpc4quantum_b200 import systems
-    if name.startswith('transmon_h'):
-        H = int(name[len('transmon_h'):])
-        return systems.config_transmon(1, horizon=H, n_steps=20, discretize=discretize), systems.ensemble_transmon
+    if name.startswith('transmon_h') or name.startswith('transmon_o2_h'):
+        order = 2 if name.startswith('transmon_o2_h') else 1
+        H = int(name.split('_h')[-1])
+        return systems.config_transmon(order, horizon=H, n_steps=20, discretize=discretize), systems.ensemble_transmon
     if name == 'qubit':
         return systems.config_qubit(1, discretize=discretize), systems.ensemble_qubit
     if name == 'crosstalk':
