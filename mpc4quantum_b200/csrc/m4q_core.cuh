@@ -44,6 +44,7 @@ template <int C_, int M_> struct Cfg {
     static constexpr int LDP = cmin(next_mod(KP, 4, 16), next_mod(KP, 12, 16));
     static constexpr int LDG = next_mod(QP, 8, 16);
     static_assert(LDP >= Q && LDP % 2 == 0, "T11 and the control columns are staged in the P buffer");
+    static_assert(QP > Q, "one padding column of G carries the affine term");
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -58,17 +59,21 @@ template <int C_, int M_> struct Cfg {
 //     (LDGSTS, 16-byte chunks), so the sweeps never wait on L2.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF> struct Rec {
-    static constexpr int K = 0;                                  // [M][N]
+    // K and B are kept in "complex pair" layout [M][C] double2: element (a, r) = (X[.][r], X[.][C + r]), so that
+    // a control row K_a (or a column of B) is read by the same complex mat-vec loop as a row of A_t.
+    static constexpr int K = 0;                                  // [M][C] pairs (K[a][r], K[a][C + r])
     static constexpr int SINV = K + rup(CF::M * CF::N, 2);       // [M][M]
     static constexpr int DV = SINV + rup(CF::M * CF::M, 2);      // [N]
-    static constexpr int B = DV + CF::N;                         // [N][M]
+    static constexpr int B = DV + CF::N;                         // [M][C] pairs (B[r][i], B[C + r][i])
     static constexpr int D = B + rup(CF::N * CF::M, 2);          // [N]
     static constexpr int SMALL = D + CF::N;                      // everything but A_t: lives in the slab ring
     static constexpr int AT = SMALL;                             // [C][C] complex: A_t = sum_k phi_k(u_t) block_k
     static constexpr int SIZE = AT + 2 * CF::C * CF::C;
-    static_assert(B % 2 == 0 && SMALL % 2 == 0, "records are moved in 16-byte chunks");
-    // during the sweeps the A_t halves of the two ring slots alias the G buffer (only live inside the factor)
-    static_assert(4 * CF::C * CF::C <= CF::KP * CF::LDG, "A_t ring does not fit the G buffer");
+    static_assert(B % 2 == 0 && SMALL % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
+    // offset of K[a][k] / B[k][i] (k = realified state index) inside their pair blocks
+    __host__ __device__ static constexpr int pair(int ctl, int k) { return (ctl * CF::C + (k % CF::C)) * 2 + (k >= CF::C); }
+    // during the vector sweeps whole records are staged in the [G | W] buffers (only live inside the factor)
+    static_assert(2 * SIZE <= (CF::KP + CF::NP) * CF::LDG, "record ring does not fit the factor scratch");
 };
 template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
     return H * Rec<CF>::SIZE + 2 * (H + 1) * CF::N;
@@ -102,7 +107,7 @@ template <class CF> struct Slab {
         q->scr = q->W;
         take(&q->T21, M * N);
         take(&q->S, M * M);
-        take(&q->ring, 2 * Rec<CF>::SMALL);
+        take(&q->ring, 2 * (Rec<CF>::SMALL - Rec<CF>::B));   // factor: [B_t | D_t] of two stages
         take(&q->kk, H * M);
         take(&q->hl, H * M);
         take(&q->phi, H * nblk);
@@ -160,10 +165,13 @@ __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// stream doubles [first, first + count) of a record into a ring slot (first, count even); one group per call
-__device__ __forceinline__ void prefetch_rec(double *slot, const double *rec, int first, int count, int lane) {
-#pragma unroll 1
-    for (int c = lane; c < (count >> 1); c += 32) cp_async16(slot + first + 2 * c, rec + first + 2 * c);
+// stream COUNT doubles (even, compile time) global -> shared; one group per call
+template <int COUNT> __device__ __forceinline__ void prefetch_block(double *dst, const double *src, int lane) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(dst) + 16 * lane;
+    unsigned long long ga = (unsigned long long)__cvta_generic_to_global(src) + 16 * lane;
+#pragma unroll
+    for (int c = 0; c < cdiv(COUNT / 2, 32); ++c, sa += 512, ga += 512)
+        if (c * 32 + lane < COUNT / 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(ga) : "memory");
     cp_async_commit();
 }
 
@@ -313,6 +321,35 @@ __device__ __forceinline__ double cmatvec(const double2 *At, const double *x, in
     }
     return fma(sgn, q0 + q1, p0 + p1);
 }
+// The same loop with M extra rows in the lanes N .. N+M-1: row a of Ext ([M][C] pairs (e[r], e[C + r])) dotted with
+// x.  Backward sweep: Ext = B_t -> B_t^T v;  forward sweep: Ext = K_t -> K_t x.  The control-space reductions thus
+// cost no shuffle tree: lane N + a holds the result and broadcasts it.
+template <class CF, bool TRANS>
+__device__ __forceinline__ double cmatvec_ext(const double2 *At, const double2 *Ext, const double *x, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    static_assert(N + M <= 32, "no free lanes for the control rows");
+    if (lane >= N + M) return 0.0;
+    const bool ext = lane >= N;
+    const bool im = !ext && lane >= C;
+    const int r = ext ? lane - N : (im ? lane - C : lane);
+    const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
+    const double sgn = (ext || im != TRANS) ? 1.0 : -1.0;
+    const double2 *blk = ext ? Ext + r * C : At + (TRANS ? r : r * C);
+    const int stride = (!ext && TRANS) ? C : 1;
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; ++j, blk += stride) {
+        const double2 m = *blk;
+        if (j & 1) {
+            p1 = fma(m.x, xp[j], p1);
+            q1 = fma(m.y, xq[j], q1);
+        } else {
+            p0 = fma(m.x, xp[j], p0);
+            q0 = fma(m.y, xq[j], q0);
+        }
+    }
+    return fma(sgn, q0 + q1, p0 + p1);
+}
 // same product straight from the model blocks, A_t = sum_k phi_k block_k (cold paths: one call per MPC step)
 template <class CF>
 __device__ __forceinline__ double apply_A(const StageOps &ops, const double *phi_t, int t, const double *x, int lane) {
@@ -382,16 +419,17 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     }
 #pragma unroll 1
     for (int e = lane; e < KP * LDG; e += 32) s.AB[e] = 0.0;
-    prefetch_rec(s.ring + ((H - 1) & 1) * R_::SMALL, ws_rec<CF>(sr, H - 1), R_::B, R_::SMALL - R_::B, lane);
+    constexpr int BD = R_::SMALL - R_::B;   // [B_t | D_t]
+    prefetch_block<BD>(s.ring + ((H - 1) & 1) * BD, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
-        const double *slot = s.ring + (t & 1) * R_::SMALL;
+        const double *Bt = s.ring + (t & 1) * BD, *Dt = Bt + (R_::D - R_::B);
         double *rec = ws_rec<CF>(sr, t);
         cp_async_wait_all();
         __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
-        if (t > 0) prefetch_rec(s.ring + ((t - 1) & 1) * R_::SMALL, ws_rec<CF>(sr, t - 1), R_::B, R_::SMALL - R_::B, lane);
+        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * BD, ws_rec<CF>(sr, t - 1) + R_::B, lane);
         // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
         {
             constexpr int NE = cdiv(C * C, 32);
@@ -424,35 +462,25 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 }
             }
         }
-        // B~ into G[:, N:Q] and D~ into va
-        const double *Bt = slot + R_::B;
+        // B~ into G[:, N:Q]
 #pragma unroll 1
         for (int e = lane; e < N * M; e += 32) {
             const int k = e / M, i = e % M;
             const bool fixed = masked && s.mask[t * M + i] != 0;
-            s.AB[k * LDG + N + i] = fixed ? 0.0 : Bt[e];
+            s.AB[k * LDG + N + i] = fixed ? 0.0 : Bt[R_::pair(i, k)];
         }
-        if (lane < N) {
-            double dt = slot[R_::D + lane];
+        if (lane < N) {   // D~ rides along as column Q of G: W[:, Q] = P_{t+1} D~ = dv_t comes out of the first product
+            double dt = Dt[lane];
             if (masked) {
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
                     const int mk = s.mask[t * M + i];
-                    if (mk) dt = fma(Bt[lane * M + i], mk == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
+                    if (mk) dt = fma(Bt[R_::pair(i, lane)], mk == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
                 }
             }
-            s.va[lane] = dt;
+            s.AB[lane * LDG + Q] = dt;
         }
         __syncwarp();
-        if (lane < N) {   // dv_t = P_{t+1} D~   (P symmetric: column access is conflict free)
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < N; j += 2) {
-                a0 = fma(s.P[j * LDP + lane], s.va[j], a0);
-                a1 = fma(s.P[(j + 1) * LDP + lane], s.va[j + 1], a1);
-            }
-            rec[R_::DV + lane] = a0 + a1;
-        }
         // ---- W = P G : MT x QT tiles, KS k-steps (rolled: the hot code has to fit the instruction cache)
         {
             double w[MT][QT][2];
@@ -481,6 +509,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 for (int ni = 0; ni < QT; ++ni) wd[(mi * 8 * LDG + ni * 8) >> 1] = make_double2(w[mi][ni][0], w[mi][ni][1]);
         }
         __syncwarp();
+        if (lane < N) rec[R_::DV + lane] = s.W[lane * LDG + Q];
         // ---- T = G^T W, upper block triangle: tile (mi <= ni) holds T[mi*8 + g8][ni*8 + 2*c4 + {0,1}].
         // T11 goes into the P buffer (P_{t+1} is dead: it was the A operand of the first product), the control
         // columns T12 = T21^T and T22 into their own small arrays.
@@ -553,7 +582,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 double kv = 0.0;
 #pragma unroll
                 for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + lane], kv);
-                rec[R_::K + a * N + lane] = kv;
+                rec[R_::K + R_::pair(a, lane)] = kv;
                 s.W[a * N + lane] = kv;   // W is dead after the second product
             }
         }
@@ -574,18 +603,13 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     __syncwarp();
 }
 
-// stream stage record t into its ring slot: doubles [first, SMALL) into the slab ring, A_t into the G buffer
+// stage record t of the workspace -> slot (t & 1) of the record ring in the [G | W] buffers
+template <class CF> __device__ __forceinline__ double *rec_slot(const Slab<CF> &s, int t) {
+    return s.AB + (t & 1) * Rec<CF>::SIZE;
+}
 template <class CF>
-__device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int first, int lane) {
-    using R_ = Rec<CF>;
-    const double *rec = ws_rec<CF>(sr, t);
-    double *sm = s.ring + (t & 1) * R_::SMALL;
-#pragma unroll 1
-    for (int c = lane; c < ((R_::SMALL - first) >> 1); c += 32) cp_async16(sm + first + 2 * c, rec + first + 2 * c);
-    double *at = s.AB + (t & 1) * (2 * CF::C * CF::C);
-#pragma unroll 1
-    for (int c = lane; c < CF::C * CF::C; c += 32) cp_async16(at + 2 * c, rec + R_::AT + 2 * c);
-    cp_async_commit();
+__device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int lane) {
+    prefetch_block<Rec<CF>::SIZE>(rec_slot<CF>(s, t), ws_rec<CF>(sr, t), lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -613,7 +637,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     const bool act = lane < N;
     const bool adj = mode == SWEEP_ADJOINT;
     double *Xo = ws_Xo<CF>(sr);
-    prefetch_stage<CF>(s, sr, H - 1, 0, lane);
+    prefetch_stage<CF>(s, sr, H - 1, lane);
 #pragma unroll 1
     for (int e = lane; e < H * M; e += 32) {
         const int t = e / M, i = e % M;
@@ -656,8 +680,8 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     }
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *slot = s.ring + (t & 1) * R_::SMALL;
-        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
+        const double *slot = rec_slot<CF>(s, t);
+        const double2 *At = reinterpret_cast<const double2 *>(slot + R_::AT);
         double *vec = (t & 1) ? s.vb : s.va;
         const double v = dv_n + p, ql = ql_n;
         if (act) vec[lane] = v;
@@ -667,12 +691,18 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         }
         cp_async_wait_all();
         __syncwarp();
-        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, 0, lane);
-        double g[M];
+        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
+        double g[M], atv;
+        if constexpr (N + M <= 32) {
+            atv = cmatvec_ext<CF, true>(At, reinterpret_cast<const double2 *>(slot + R_::B), vec, lane);
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = act ? slot[R_::B + lane * M + i] * v : 0.0;
-        warp_sum_vec<M>(g, lane);
-        const double atv = cmatvec<CF, true>(At, vec, lane);
+            for (int i = 0; i < M; ++i) g[i] = __shfl_sync(FULL, atv, N + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < M; ++i) g[i] = act ? slot[R_::B + R_::pair(i, lane)] * v : 0.0;
+            warp_sum_vec<M>(g, lane);
+            atv = cmatvec<CF, true>(At, vec, lane);
+        }
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             g[i] = (!adj && s.mask[t * M + i]) ? 0.0 : g[i] - s.hl[t * M + i];
@@ -685,9 +715,9 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             for (int b = 0; b < M; ++b) kkv = fma(adj ? (b == lane ? 1.0 : 0.0) : slot[R_::SINV + lane * M + b], g[b], kkv);
             s.kk[t * M + lane] = kkv;
         }
-        if (!adj) {
+        if (!adj && act) {
 #pragma unroll
-            for (int a = 0; a < M; ++a) pn = fma(act ? -slot[R_::K + a * N + lane] : 0.0, g[a], pn);
+            for (int a = 0; a < M; ++a) pn = fma(-slot[R_::K + R_::pair(a, lane)], g[a], pn);
         }
         p = pn;
     }
@@ -698,18 +728,24 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     if (WRITE_X && act) Xo[lane] = x;
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
-        const double *slot = s.ring + (t & 1) * R_::SMALL;
-        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
+        const double *slot = rec_slot<CF>(s, t);
+        const double2 *At = reinterpret_cast<const double2 *>(slot + R_::AT);
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) vec[lane] = x;
         cp_async_wait_all();
         __syncwarp();
-        if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, 0, lane);
-        double u[M];
+        if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, lane);
+        double u[M], ax;
+        if constexpr (N + M <= 32) {
+            ax = cmatvec_ext<CF, false>(At, reinterpret_cast<const double2 *>(slot + R_::K), vec, lane);
 #pragma unroll
-        for (int a = 0; a < M; ++a) u[a] = act ? slot[R_::K + a * N + lane] * x : 0.0;
-        warp_sum_vec<M>(u, lane);
-        const double ax = cmatvec<CF, false>(At, vec, lane);
+            for (int a = 0; a < M; ++a) u[a] = __shfl_sync(FULL, ax, N + a);
+        } else {
+#pragma unroll
+            for (int a = 0; a < M; ++a) u[a] = act ? slot[R_::K + R_::pair(a, lane)] * x : 0.0;
+            warp_sum_vec<M>(u, lane);
+            ax = cmatvec<CF, false>(At, vec, lane);
+        }
 #pragma unroll
         for (int a = 0; a < M; ++a) u[a] = s.mask[t * M + a] ? s.hl[t * M + a] : -u[a] - s.kk[t * M + a];
         if (lane < M) {
@@ -721,7 +757,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         if (act) {
             double xn = ax + slot[R_::D + lane];
 #pragma unroll
-            for (int a = 0; a < M; ++a) xn = fma(slot[R_::B + lane * M + a], u[a], xn);
+            for (int a = 0; a < M; ++a) xn = fma(slot[R_::B + R_::pair(a, lane)], u[a], xn);
             x = xn;
             if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
@@ -749,7 +785,7 @@ __device__ __forceinline__ double apply_Q(const double *Qm, int q_diag, const do
 // Adjoint gradient of the condensed cost at (Xo, Uo) -> s.kk[t*M+i] (re-used as scratch); returns max |grad|.
 //   lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};  lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}
 // General (non-diagonal cost) version; the diagonal case runs as a mode of riccati_solve.
-// B_t, A_t through the ring, x_t - r_t register-prefetched; vectors double-buffered (va/vb, and W as scratch).
+// B_t, A_t through the ring, x_t - r_t register-prefetched; vectors double-buffered (va/vb, and P as scratch).
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
 __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in, int lane) {
@@ -760,20 +796,20 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
     const int H = sr.H;
     const bool act = lane < N;
     const double *Xo = ws_Xo<CF>(sr);
-    prefetch_stage<CF>(s, sr, H - 1, R_::B, lane);
+    prefetch_stage<CF>(s, sr, H - 1, lane);
     double xd_n = act ? Xo[(H - 1) * N + lane] - qp.r[(H - 1) * N + lane] : 0.0;
-    if (act) s.W[lane] = Xo[H * N + lane] - qp.r[H * N + lane];
+    if (act) s.P[lane] = Xo[H * N + lane] - qp.r[H * N + lane];   // P is dead outside the factor
     __syncwarp();
-    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.W, lane);
+    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.P, lane);
     double gmax = 0.0;
     __syncwarp();
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *Bt = s.ring + (t & 1) * R_::SMALL + R_::B;
-        const double2 *At = reinterpret_cast<const double2 *>(s.AB + (t & 1) * (2 * C * C));
+        const double *Bt = rec_slot<CF>(s, t) + R_::B;
+        const double2 *At = reinterpret_cast<const double2 *>(rec_slot<CF>(s, t) + R_::AT);
         const double *Rt = qp.R + t * qp.r_stride;
         double *lamv = (t & 1) ? s.vb : s.va;
-        double *xdv = s.W + (t & 1) * N;
+        double *xdv = s.P + (t & 1) * N;
         const double xd = xd_n;
         if (act) {
             lamv[lane] = lam;
@@ -782,10 +818,10 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
         }
         cp_async_wait_all();
         __syncwarp();
-        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, R_::B, lane);
+        if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
         double g[M];
 #pragma unroll
-        for (int i = 0; i < M; ++i) g[i] = act ? Bt[lane * M + i] * lam : 0.0;
+        for (int i = 0; i < M; ++i) g[i] = act ? Bt[R_::pair(i, lane)] * lam : 0.0;
         warp_sum_vec<M>(g, lane);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
@@ -880,7 +916,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 if (lane < N) {
                     double xn = ax + rec[Rec<CF>::D + lane];
 #pragma unroll
-                    for (int a = 0; a < M; ++a) xn = fma(rec[Rec<CF>::B + lane * M + a], s.Uo[t * M + a], xn);
+                    for (int a = 0; a < M; ++a) xn = fma(rec[Rec<CF>::B + Rec<CF>::pair(a, lane)], s.Uo[t * M + a], xn);
                     x = xn;
                     Xo[(t + 1) * N + lane] = x;
                 }
@@ -1087,7 +1123,7 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
             double d = 0.0;
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                rec[R_::B + lane * M + i] = b[i];
+                rec[R_::B + R_::pair(i, lane)] = b[i];
                 d = fma(-b[i], s.Ug[t * M + i], d);
             }
             rec[R_::D + lane] = d;

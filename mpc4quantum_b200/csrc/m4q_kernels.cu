@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         for (int e = lane; e < H * N * M; e += 32) {
             const int t = e / (N * M), rem = e % (N * M), kk = rem / M, i = rem % M;
             const double2 v = Bk[((size_t)t * C + kk % C) * M + i];
-            ws_rec<CF>(sr, t)[Rec<CF>::B + rem] = kk < C ? v.x : v.y;
+            ws_rec<CF>(sr, t)[Rec<CF>::B + Rec<CF>::pair(i, kk)] = kk < C ? v.x : v.y;
         }
 #pragma unroll 1
         for (int e = lane; e < H * N; e += 32) {
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs 
         for (int e = lane; e < H * C * M; e += 32) {
             const int t = e / (C * M), rem = e % (C * M), r = rem / M, i = rem % M;
             const double *rec = ws_rec<CF>(sr, t);
-            Bo[e] = make_double2(rec[Rec<CF>::B + r * M + i], rec[Rec<CF>::B + (C + r) * M + i]);
+            Bo[e] = make_double2(rec[Rec<CF>::B + Rec<CF>::pair(i, r)], rec[Rec<CF>::B + Rec<CF>::pair(i, C + r)]);
         }
 #pragma unroll 1
         for (int e = lane; e < H * C; e += 32) {
