@@ -53,7 +53,7 @@ template <int C_, int M_> struct Cfg {
 //     trajectories and a few vectors -- 13 KB for the transmon, (almost) independent of the horizon, so that
 //     ~16 members are resident per SM;
 //   * L2-resident workspace in global memory (one per resident warp, re-used member after member): the
-//     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t | A_t], then the state trajectories
+//     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t | A_t | x_t - r_t], then the trajectories
 //     Xg, Xo [(H+1) N].  Records are written with plain stores where they are produced (factor: K, S^-1, dv;
 //     linearisation: B, D) and streamed back one stage ahead of their use through the ring with cp.async
 //     (LDGSTS, 16-byte chunks), so the sweeps never wait on L2.
@@ -66,9 +66,10 @@ template <class CF> struct Rec {
     static constexpr int DV = SINV + rup(CF::M * CF::M, 2);      // [N]
     static constexpr int B = DV + CF::N;                         // [M][C] pairs (B[r][i], B[C + r][i])
     static constexpr int D = B + rup(CF::N * CF::M, 2);          // [N]
-    static constexpr int SMALL = D + CF::N;                      // everything but A_t: lives in the slab ring
+    static constexpr int SMALL = D + CF::N;                      // end of the part the factor reads back ([B | D])
     static constexpr int AT = SMALL;                             // [C][C] complex: A_t = sum_k phi_k(u_t) block_k
-    static constexpr int SIZE = AT + 2 * CF::C * CF::C;
+    static constexpr int XC = AT + 2 * CF::C * CF::C;            // [N] x_t - r_t of the last rollout (adjoint sweep)
+    static constexpr int SIZE = XC + CF::N;
     static_assert(B % 2 == 0 && SMALL % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
     // offset of K[a][k] / B[k][i] (k = realified state index) inside their pair blocks
     __host__ __device__ static constexpr int pair(int ctl, int k) { return (ctl * CF::C + (k % CF::C)) * 2 + (k >= CF::C); }
@@ -80,7 +81,7 @@ template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
 }
 
 template <class CF> struct Slab {
-    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *lo0, *hi0, *xcur, *xmeas, *scr;
+    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr;
     int *mask;
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
@@ -118,6 +119,7 @@ template <class CF> struct Slab {
         take(&q->x0, N);
         take(&q->va, N);
         take(&q->vb, N);
+        take(&q->xT, N);
         take(&q->lo0, M);
         take(&q->hi0, M);
         take(&q->xcur, 2 * dd);
@@ -593,7 +595,8 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
         for (int q = 0; q < NPAIR; ++q) {
             if (pair[q] < 0) continue;
             const int i = pair[q] >> 8, j = pair[q] & 255;
-            double v = s.P[i * LDP + j] + Qt[i * N + j];
+            double v = s.P[i * LDP + j];
+            if (!qp.q_diag || i == j) v += Qt[i * N + j];
 #pragma unroll
             for (int a = 0; a < M; ++a) v = fma(-s.T21[a * N + i], s.W[a * N + j], v);
             s.P[i * LDP + j] = v;
@@ -616,7 +619,7 @@ __device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef 
 // Vector sweeps.  One routine, three modes (one copy of the code in the instruction cache):
 //   SWEEP_ADMM    backward costate + forward rollout of the ADMM u-update (mask must be all zero)
 //   SWEEP_POLISH  the same with the controls of the working set (mask != 0) pinned to their bound
-//   SWEEP_ADJOINT backward only: adjoint gradient of the condensed cost at (Xo, Uo) -> kk, returns max |grad|
+//   SWEEP_ADJOINT backward only: adjoint gradient of the condensed cost at the last rollout -> kk, returns max |grad|
 //                 lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};
 //                 lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}          (diagonal costs; else adjoint_gradient())
 // All three are the recursion  v = dv + p;  g = B^T v - h;  p <- A^T v - q - K^T g  with different (dv, h, q, K).
@@ -667,31 +670,32 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         }
         s.hl[e] = h;
     }
-    // q_t per lane: Qbar_t r_t (table) for the Riccati modes, -2 Qbar_t (x_t - r_t) for the adjoint (diagonal Qbar)
-    auto q_of = [&](int t) -> double {
-        if (!adj) return qp.qlin[t * N + lane];
-        return -2.0 * qp.Q[t * qp.q_stride + lane * N + lane] * (Xo[t * N + lane] - qp.r[t * N + lane]);
-    };
+    // q_t per lane: Qbar_t r_t (table, register-prefetched) for the Riccati modes; the adjoint takes
+    // -2 Qbar_t (x_t - r_t) (diagonal Qbar) from the record, where the last rollout left x_t - r_t
     double p = 0.0, dv_n = 0.0, ql_n = 0.0, gmax = 0.0;
     if (act) {
-        p = adj ? 2.0 * qp.Qf[lane * N + lane] * (Xo[H * N + lane] - qp.r[H * N + lane]) : -qp.qlinf[lane];
-        if (!adj) dv_n = ws_rec<CF>(sr, H - 1)[R_::DV + lane];
-        ql_n = q_of(H - 1);
+        p = adj ? 2.0 * qp.Qf[lane * N + lane] * s.xT[lane] : -qp.qlinf[lane];
+        if (!adj) {
+            dv_n = ws_rec<CF>(sr, H - 1)[R_::DV + lane];
+            ql_n = qp.qlin[(H - 1) * N + lane];
+        }
     }
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *slot = rec_slot<CF>(s, t);
         const double2 *At = reinterpret_cast<const double2 *>(slot + R_::AT);
         double *vec = (t & 1) ? s.vb : s.va;
-        const double v = dv_n + p, ql = ql_n;
+        const double v = dv_n + p;
+        double ql = ql_n;
         if (act) vec[lane] = v;
-        if (t > 0 && act) {
-            if (!adj) dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
-            ql_n = q_of(t - 1);
+        if (t > 0 && act && !adj) {
+            dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
+            ql_n = qp.qlin[(t - 1) * N + lane];
         }
         cp_async_wait_all();
         __syncwarp();
         if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
+        if (adj && act) ql = -2.0 * qp.Q[t * qp.q_stride + lane * N + lane] * slot[R_::XC + lane];
         double g[M], atv;
         if constexpr (N + M <= 32) {
             atv = cmatvec_ext<CF, true>(At, reinterpret_cast<const double2 *>(slot + R_::B), vec, lane);
@@ -731,7 +735,10 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         const double *slot = rec_slot<CF>(s, t);
         const double2 *At = reinterpret_cast<const double2 *>(slot + R_::AT);
         double *vec = (t & 1) ? s.vb : s.va;
-        if (act) vec[lane] = x;
+        if (act) {
+            vec[lane] = x;
+            if (WRITE_X) ws_rec<CF>(sr, t)[R_::XC + lane] = x - qp.r[t * N + lane];
+        }
         cp_async_wait_all();
         __syncwarp();
         if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, lane);
@@ -762,8 +769,10 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
     }
+    if (act) s.xT[lane] = x - qp.r[H * N + lane];
     __syncwarp();
-    return 0.0;
+    // a non-finite state anywhere in the rollout propagates to x_H
+    return __any_sync(FULL, !isfinite(x)) ? 1.0 : 0.0;
 }
 
 // (Qbar v)[lane] for v in shared memory
@@ -873,6 +882,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     cnt.solves++;
     double eps = set.eps;
     int status = 0;
+    bool x_nonfinite = false;   // a non-finite state of the reported rollout (it propagates to x_H)
     bool run_admm = !set.polish || set.admm_first;
     for (;;) {
         if (run_admm) {
@@ -922,6 +932,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 }
                 __syncwarp();
             }
+            x_nonfinite = __any_sync(FULL, !isfinite(x));
             break;
         }
         // ---- working set from the (z, y) estimate: at a bound with the multiplier pushing outwards
@@ -940,7 +951,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             riccati_factor<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
             cnt.factor++;
             cnt.polish++;
-            riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_POLISH, true, lane);
+            x_nonfinite = riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_POLISH, true, lane) != 0.0;
             const double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
                                            : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             const double gs = fmax(1.0, gmax);
@@ -998,12 +1009,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     bool nonfinite = false;
 #pragma unroll 1
     for (int e = lane; e < HM; e += 32) nonfinite |= !isfinite(s.Uo[e]);
-    {
-        const double *Xo = ws_Xo<CF>(sr);
-#pragma unroll 1
-        for (int e = lane; e < (H + 1) * N; e += 32) nonfinite |= !isfinite(Xo[e]);
-    }
-    if (__any_sync(FULL, nonfinite)) status = 3;
+    if (__any_sync(FULL, nonfinite) || x_nonfinite) status = 3;
     return status;
 }
 

@@ -363,10 +363,21 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                         line_search<CF, true>(sr, qp, lane, alpha, stp);        // mpc.py:215
                         done = stp < 1e-4;                                      // mpc.py:224
                     }
-#pragma unroll 4
-                    for (int e = lane; e < (H + 1) * N; e += 32) {
-                        const double xg = Xg[e];
-                        Xg[e] = fma(alpha, Xo[e] - xg, xg);
+                    // guess update, four independent elements in flight (the arrays live in L2)
+#pragma unroll 1
+                    for (int e0 = lane; e0 < (H + 1) * N; e0 += 128) {
+                        double xg[4], xo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int e = e0 + 32 * q;
+                            xg[q] = e < (H + 1) * N ? Xg[e] : 0.0;
+                            xo[q] = e < (H + 1) * N ? Xo[e] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int e = e0 + 32 * q;
+                            if (e < (H + 1) * N) Xg[e] = fma(alpha, xo[q] - xg[q], xg[q]);
+                        }
                     }
 #pragma unroll 1
                     for (int e = lane; e < H * M; e += 32) s.Ug[e] = fma(alpha, s.Uo[e] - s.Ug[e], s.Ug[e]);
