@@ -26,7 +26,8 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 // The two dense products of a Riccati stage, W = P G and T = G^T W with G = [A_t | B_t] (N x Q), run on the fp64
 // tensor cores (mma.sync m8n8k4, "DMMA"): operands padded to NP = rup(N, 8) rows, QP = rup(Q, 8) columns and
 // KP = rup(N, 4) in the contraction; leading dimensions chosen so that the fragment loads are free of bank
-// conflicts (A-type loads: ld = 4 or 12 mod 16; B-type loads: ld = 8 mod 16).
+// conflicts: a 64-bit warp load is served per half warp (fragment rows 0..3 x columns 0..3), which wants the row
+// stride to be 4 or 12 mod 16 doubles for both the A-type (row = lane/4) and the B-type (row = lane%4) pattern.
 // MAXW: most warps (members) a CTA is ever launched with; it fixes the register budget (__launch_bounds__).
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r - x % m) % m + m) % m; }
@@ -42,7 +43,7 @@ template <int C_, int M_> struct Cfg {
     static constexpr int NP = rup(N, 8), QP = rup(Q, 8), KP = rup(N, 4);
     static constexpr int MT = NP / 8, QT = QP / 8, KS = KP / 4;   // tile counts
     static constexpr int LDP = cmin(next_mod(KP, 4, 16), next_mod(KP, 12, 16));
-    static constexpr int LDG = next_mod(QP, 8, 16);
+    static constexpr int LDG = cmin(next_mod(QP, 4, 16), next_mod(QP, 12, 16));
     static_assert(LDP >= Q && LDP % 2 == 0, "T11 and the control columns are staged in the P buffer");
     static_assert(QP > Q, "one padding column of G carries the affine term");
 };
