@@ -333,6 +333,17 @@ def main():
     out_bytes = fid_out.numel() * 8 + ec_out.numel() * 4 + us_out.numel() * 8
     hbm_alg = in_bytes + res.xs.numel() * 16 + out_bytes + counters.nbytes + qp_count.nbytes
 
+    # DRAM traffic of the dominant kernel: from the committed ncu capture (profiles/), scaled to this launch's members
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_final_ncu_traffic.json')) as fh:
+            tr = json.load(fh)
+        if args.workload == 'transmon_h16':
+            traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * n / tr['members']
+            traffic_src = ('ncu dram__bytes_read.sum + dram__bytes_write.sum of one %d-member launch '
+                           '(profiles/r1_final_ncu_traffic.json), scaled by members' % tr['members'])
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -354,7 +365,7 @@ def main():
                 'd2h_bytes_per_step': int(out_bytes)},
         'gpu_launches': 3 * args.steps,     # build_tables + mpc_kernel + hist_kernel per pass
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / fp64_peak, 'traffic': None,
+                     'frac': achieved / fp64_peak, 'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_source': 'm4q_fp64_fma_probe measured in this run (MEASURED_PEAKS.json has no fp64 figure)',
                      'dmma_probe_tflops': dmma_peak,
                      'kernel': 'mpc_kernel', 'kernel_ms': kernel_ms, 'flops_per_launch': flops,

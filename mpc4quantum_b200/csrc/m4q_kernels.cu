@@ -1079,8 +1079,40 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
                                     reinterpret_cast<const double2 *>(p->Qf), p->R,
                                     reinterpret_cast<const double2 *>(p->X_targ), p->U_targ, a.tab);
     M4Q_CUDA(cudaGetLastError());
+    // The workspaces are rewritten every QP; ask L2 to keep them (persisting lines) instead of writing them back to
+    // HBM.  Best effort: M4Q_L2_PERSIST=0 switches it off, failures are ignored.
+    bool window = false;
+    const char *pv = getenv("M4Q_L2_PERSIST");
+    if (!pv || atoi(pv) != 0) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t ws_bytes = (size_t)g.ctas * g.warps * ws_doubles<CF>(p->horizon) * sizeof(double);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t want = ws_bytes < (size_t)max_persist ? ws_bytes : (size_t)max_persist;
+            static size_t reserved = 0;
+            if (want > reserved && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) reserved = want;
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = a.ws;
+            attr.accessPolicyWindow.num_bytes = ws_bytes < (size_t)max_window ? ws_bytes : (size_t)max_window;
+            attr.accessPolicyWindow.hitRatio = reserved >= ws_bytes ? 1.0f : (float)reserved / (float)ws_bytes;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        }
+        cudaGetLastError();
+    }
     mpc_kernel<CF><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
     M4Q_CUDA(cudaGetLastError());
+    if (window) {   // do not leave the window on the caller's stream
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     return 0;
 }
 
