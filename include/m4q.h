@@ -159,6 +159,12 @@ int m4q_line_search_batched(int64_t N, int32_t c, int32_t m, int32_t H,
  *   LIFTED model states which the caller writes into xs[:, :, step_begin] before each single-step launch
  *   (host-stepped mode for a user-defined Experiment.simulate / exit_condition; mpc.py:247-292 stay on the host).
  *   state: m4q_mpc_state_bytes(prob, N) bytes, carries guesses and ADMM duals between launches.
+ *   tables: m4q_mpc_table_bytes(prob) bytes of device memory, owned by the caller, re-usable across launches of the
+ *   same problem: the member-independent tables (realified costs, targets) followed by one L2-resident workspace
+ *   per resident warp (stage records [K | S^-1 | dv | B | D | A_t | x - r] and the state trajectories of the member
+ *   the warp is working on; sized for the widest launch on the current device, independent of N).
+ *   Environment (measurement aids): M4Q_MAX_WARPS caps the members per CTA; M4Q_L2_PERSIST=0 disables the
+ *   persisting-L2 access-policy window that the launch sets on `stream` for the workspaces.
  */
 int64_t m4q_mpc_state_bytes(const m4q_mpc_problem *prob_host, int64_t N);
 int64_t m4q_mpc_table_bytes(const m4q_mpc_problem *prob_host);
