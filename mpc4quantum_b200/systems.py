@@ -178,6 +178,76 @@ def config_crosstalk(crosstalk=0.0, wiring='consistent', n_steps=50, discretize=
                  warm_start=False, target=target_plant, nominal=qubits, kind='coupled')
 
 
+def config_qubit_freq(order=1, n_steps=100, discretize=None):
+    """tests/test_mpc4quantum.py:705-768 (test_NOT_state_freq): the qubit of config 1 with dt = 0.2, H = 50 and one
+    plant measurement every 5 MPC steps (model steps in between, mpc.py:252-267)."""
+    clock = StepClock(dt=0.2, horizon=50, n_steps=n_steps)
+    clock.measure_freq = 5
+    sat = 2 * np.pi * 0.1
+    du = 0.1 * sat
+    wq = 2 * np.pi * 4
+    nominal = RWA_Qubit(wq, wq, wq)
+    A_init = (discretize or discretize_homogeneous)([liouvillian(h) for h in nominal.H_list], clock.dt, order)
+    plant = RWA_Qubit(wq * 0.99, wq, wq)
+    Q = np.diag([1.0, 0, 0, 1.0])
+    R = 1e-2 * np.eye(1)
+    Rx = rx(1e-4)
+    rho0 = Rx @ proj(2, 0) @ Rx.conj().T
+    target = proj(2, 1).reshape(-1)
+    S, H = clock.n_steps, clock.horizon
+    return _pack(name='qubit_freq', x0=rho0.reshape(-1), dim_u=1, order=order,
+                 X_targ=np.tile(target[:, None], (1, S + H + 1)), U_targ=np.zeros((1, S + H)),
+                 clock=clock, experiment=plant.QE, model=_dmdc(A_init, 4), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=True, target=target, wq=wq, nominal=nominal)
+
+
+def config_cnot(n_steps=200, horizon=50, ramp_steps=None, discretize=None):
+    """tests/test_mpc4quantum.py:399-466 (test_CNOT_state): two coupled qubits, fully vectorised 16-dim density
+    matrix, three controls, ramped target (so the lagging target windows of mpc.py:276-277 matter)."""
+    clock = StepClock(dt=0.25, horizon=horizon, n_steps=n_steps)
+    sat = 2 * np.pi * 0.05
+    du = 1 * sat
+    qubits = RWA_Coupled()
+    A_init = (discretize or discretize_homogeneous)([liouvillian(h) for h in qubits.H_list], clock.dt, 1)
+    Rx1, Rx2 = rx(-1e-2), rx(1e-2)
+    rho0 = np.kron(Rx1 @ proj(2, 0) @ Rx1.conj().T, Rx2 @ proj(2, 0) @ Rx2.conj().T)
+    target = np.kron(proj(2, 0), proj(2, 1)).reshape(-1)
+    S, H = clock.n_steps, clock.horizon
+    ramp = ramp_steps or S
+    incline = np.array([min(1.0, 2 * n / ramp) for n in range(S + H + 1)])
+    Q = np.zeros((16, 16))
+    for i in (0, 5, 10, 15):
+        Q[i, i] = 1
+    R = 1e-3 * np.eye(3)
+    return _pack(name='cnot', x0=rho0.reshape(-1), dim_u=3, order=1,
+                 X_targ=target[:, None] * incline[None, :], U_targ=np.zeros((3, S + H)),
+                 clock=clock, experiment=qubits.QE, model=_dmdc(A_init, 16), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=True, target=target, nominal=qubits)
+
+
+def config_transmon_reduced(n_steps=20, horizon=10, discretize=None):
+    """A two-level model (controls sx/2, sy/2) steering the three-level transmon of config 3 observed only in its
+    qubit block (QExperiment32, experiment.py:215-235; util_qubits.py:119-138)."""
+    clock = StepClock(dt=0.25, horizon=horizon, n_steps=n_steps)
+    sat = 2 * np.pi * 0.25
+    du = 0.5 * sat
+    anharm = -2 * np.pi * 0.1 * (1 / clock.dt)
+    plant = RWA_Transmon_Reduced(alpha=anharm)
+    H_model = [0 * I2, 0.5 * SX, 0.5 * SY]
+    A_init = (discretize or discretize_homogeneous)([liouvillian(h) for h in H_model], clock.dt, 1)
+    Q = np.diag([1.0, 0, 0, 1.0])
+    R = (1e-3 / sat ** 2) * np.eye(2)
+    Rx = rx(1e-4)
+    rho0 = proj(3, 0)
+    rho0[:2, :2] = Rx.conj().T @ rho0[:2, :2] @ Rx
+    target = proj(2, 1).reshape(-1)
+    S, H = clock.n_steps, clock.horizon
+    return _pack(name='transmon_reduced', x0=rho0.reshape(-1), dim_u=2, order=1,
+                 X_targ=np.tile(target[:, None], (1, S + H + 1)), U_targ=np.zeros((2, S + H)),
+                 clock=clock, experiment=plant.QE, model=_dmdc(A_init, 4), Q=Q, R=R, Qf=Q, sat=sat, du=du,
+                 warm_start=True, target=target, nominal=plant, kind='trunc32')
+
+
 def _dmdc(A_full, c):
     p = A_full.shape[1] // c - 1
     return DMDc(c, c, c * p, A_full)

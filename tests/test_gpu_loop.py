@@ -227,3 +227,43 @@ def test_order1_cost_to_go_overflow_is_reported_not_hidden():
         assert xs.shape[1] == us.shape[1] + 1 < 7
         xs_c, us_c, ec_c, _ = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list)
         assert np.abs(us - us_c[:, :us.shape[1]]).max() < U_TOL      # every step it did return is right
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The rest of the reference's state-preparation matrix: other kernel instantiations
+# ----------------------------------------------------------------------------------------------------------
+def test_cnot_state_16dim_three_controls():
+    """tests/test_mpc4quantum.py:399-466: c = 16, m = 3 (n = 32: every lane a state row), H = 50, ramped target."""
+    cfg = systems.config_cnot(n_steps=5, horizon=50, ramp_steps=200)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    xs_c, us_c, ec_c, stats = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list)
+    assert ec == 0 == ec_c
+    assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
+    assert np.abs(xs - xs_c).max() < 10 * U_TOL
+
+
+@pytest.mark.parametrize('order', [1, 2])
+def test_not_state_measure_freq_5(order):
+    """tests/test_mpc4quantum.py:705-768: plant measured every 5th step, newest-first control window (mpc.py:257),
+    model steps in between (mpc.py:264-267)."""
+    cfg = systems.config_qubit_freq(order, n_steps=20)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    xs_c, us_c, ec_c, stats = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list)
+    assert ec == 0 == ec_c
+    assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
+    assert np.abs(xs - xs_c).max() < 10 * U_TOL
+
+
+def test_qutrit_plant_observed_in_qubit_block():
+    """QExperiment32 (experiment.py:215-235): c = 4, m = 2, plant d = 3, truncate-and-renormalise lift."""
+    from oracle import restate as rs
+    cfg = systems.config_transmon_reduced(n_steps=12)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    xs_c, us_c, ec_c, stats = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list, rs.lift_32, rs.lift_identity)
+    assert ec == 0 == ec_c
+    assert xs.shape == (9, 13)
+    assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
+    assert np.abs(xs - xs_c).max() < 10 * U_TOL
