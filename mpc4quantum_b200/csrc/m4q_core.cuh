@@ -269,6 +269,18 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
 
 // inverse of a small symmetric positive definite matrix held in registers (Gauss-Jordan, no pivoting)
 template <int M> __device__ __forceinline__ void spd_inverse(double (&a)[M][M], double (&inv)[M][M]) {
+    if constexpr (M == 1) {
+        inv[0][0] = 1.0 / a[0][0];
+        return;
+    }
+    if constexpr (M == 2) {   // adjugate / determinant: one division
+        const double r = 1.0 / fma(a[0][0], a[1][1], -a[0][1] * a[1][0]);
+        inv[0][0] = a[1][1] * r;
+        inv[1][1] = a[0][0] * r;
+        inv[0][1] = -a[0][1] * r;
+        inv[1][0] = -a[1][0] * r;
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -536,21 +548,32 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll
                     for (int ni = mi; ni < QT; ++ni) dmma(tt[mi][ni], af[mi], bf[ni]);
             }
+            // publish, branch free: elements outside T11 / T12 / T22 go to a dummy slot (va is unused in the factor)
 #pragma unroll
             for (int mi = 0; mi < QT; ++mi)
 #pragma unroll
                 for (int ni = mi; ni < QT; ++ni) {
                     const int i = mi * 8 + g8, j = ni * 8 + 2 * c4;   // N and j even: the pair (j, j+1) is on one side
-                    if (j < N) {
-                        if (i < N) *reinterpret_cast<double2 *>(s.P + i * LDP + j) = make_double2(tt[mi][ni][0], tt[mi][ni][1]);
+                    if (ni * 8 + 7 < N) {          // whole tile left of the control columns (compile time)
+                        double *dst = (mi * 8 + 7 < N || i < N) ? s.P + i * LDP + j : s.va;
+                        *reinterpret_cast<double2 *>(dst) = make_double2(tt[mi][ni][0], tt[mi][ni][1]);
                     } else {
+                        if (ni * 8 < N) {          // tile straddles: its left pairs still belong to T11
+                            double *dst = (j < N && i < N) ? s.P + i * LDP + j : s.va;
+                            *reinterpret_cast<double2 *>(dst) = make_double2(tt[mi][ni][0], tt[mi][ni][1]);
+                        }
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            if (j + e >= Q) continue;
-                            if (i < N) s.T21[(j + e - N) * N + i] = tt[mi][ni][e];
-                            else if (i <= j + e) {
-                                s.S[(i - N) * M + (j + e - N)] = tt[mi][ni][e];
-                                s.S[(j + e - N) * M + (i - N)] = tt[mi][ni][e];
+                            const int jj = j + e;
+                            const bool ctl = jj >= N && jj < Q;
+                            double *d1 = (ctl && i < N) ? s.T21 + (jj - N) * N + i : s.va + 2;
+                            *d1 = tt[mi][ni][e];
+                            if (mi == ni || (mi * 8 + 7 >= N)) {   // rows that can reach into T22 (compile time)
+                                const bool s22 = ctl && i >= N && i <= jj;
+                                double *d2 = s22 ? s.S + (i - N) * M + (jj - N) : s.va + 3;
+                                double *d3 = s22 ? s.S + (jj - N) * M + (i - N) : s.va + 3;
+                                *d2 = tt[mi][ni][e];
+                                *d3 = tt[mi][ni][e];
                             }
                         }
                     }
@@ -697,6 +720,15 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         __syncwarp();
         if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
         if (adj && act) ql = -2.0 * qp.Q[t * qp.q_stride + lane * N + lane] * slot[R_::XC + lane];
+        // control-space operands first: their latency hides behind the mat-vec
+        int mk[M];
+        double hv[M], kq[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            mk[i] = adj ? 0 : s.mask[t * M + i];
+            hv[i] = s.hl[t * M + i];
+            kq[i] = (!adj && act) ? slot[R_::K + R_::pair(i, lane)] : 0.0;
+        }
         double g[M], atv;
         if constexpr (N + M <= 32) {
             atv = cmatvec_ext<CF, true>(At, reinterpret_cast<const double2 *>(slot + R_::B), vec, lane);
@@ -710,8 +742,8 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         }
 #pragma unroll
         for (int i = 0; i < M; ++i) {
-            g[i] = (!adj && s.mask[t * M + i]) ? 0.0 : g[i] - s.hl[t * M + i];
-            gmax = fmax(gmax, fabs(g[i]));
+            g[i] = mk[i] ? 0.0 : g[i] - hv[i];
+            if (adj) gmax = fmax(gmax, fabs(g[i]));
         }
         double pn = atv - ql;
         if (lane < M) {
@@ -720,10 +752,8 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             for (int b = 0; b < M; ++b) kkv = fma(adj ? (b == lane ? 1.0 : 0.0) : slot[R_::SINV + lane * M + b], g[b], kkv);
             s.kk[t * M + lane] = kkv;
         }
-        if (!adj && act) {
 #pragma unroll
-            for (int a = 0; a < M; ++a) pn = fma(-slot[R_::K + R_::pair(a, lane)], g[a], pn);
-        }
+        for (int a = 0; a < M; ++a) pn = fma(-kq[a], g[a], pn);
         p = pn;
     }
     __syncwarp();   // kk complete; va/vb free again
@@ -743,6 +773,15 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         cp_async_wait_all();
         __syncwarp();
         if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, lane);
+        int mk[M];
+        double hv[M], bq[M];
+        const double dq = act ? slot[R_::D + lane] : 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            mk[a] = s.mask[t * M + a];
+            hv[a] = mk[a] ? s.hl[t * M + a] : -s.kk[t * M + a];
+            bq[a] = act ? slot[R_::B + R_::pair(a, lane)] : 0.0;
+        }
         double u[M], ax;
         if constexpr (N + M <= 32) {
             ax = cmatvec_ext<CF, false>(At, reinterpret_cast<const double2 *>(slot + R_::K), vec, lane);
@@ -755,7 +794,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             ax = cmatvec<CF, false>(At, vec, lane);
         }
 #pragma unroll
-        for (int a = 0; a < M; ++a) u[a] = s.mask[t * M + a] ? s.hl[t * M + a] : -u[a] - s.kk[t * M + a];
+        for (int a = 0; a < M; ++a) u[a] = mk[a] ? hv[a] : hv[a] - u[a];
         if (lane < M) {
             double uv = u[0];
 #pragma unroll
@@ -763,9 +802,9 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             s.Uo[t * M + lane] = uv;
         }
         if (act) {
-            double xn = ax + slot[R_::D + lane];
+            double xn = ax + dq;
 #pragma unroll
-            for (int a = 0; a < M; ++a) xn = fma(slot[R_::B + R_::pair(a, lane)], u[a], xn);
+            for (int a = 0; a < M; ++a) xn = fma(bq[a], u[a], xn);
             x = xn;
             if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }

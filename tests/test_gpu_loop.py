@@ -267,3 +267,19 @@ def test_qutrit_plant_observed_in_qubit_block():
     assert xs.shape == (9, 13)
     assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
     assert np.abs(xs - xs_c).max() < 10 * U_TOL
+
+
+def test_transmon_bitwise_repeatable_across_batch_compositions():
+    """Race canary for the warp-private pipeline (cp.async ring, double-buffered vectors, DMMA staging): the same
+    member must come out bit for bit whichever warp, CTA and workspace slot it lands on (compute-sanitizer is closed
+    on this pool, so determinism under re-scheduling is the available evidence)."""
+    cfg = systems.config_transmon(1)
+    ens, _ = systems.ensemble_transmon(65536)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    a = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 4000), *args[7:], fid_target=cfg['target'], **kw)
+    b = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(1500, 1700), *args[7:], fid_target=cfg['target'], **kw)
+    c = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 4000), *args[7:], fid_target=cfg['target'], **kw)
+    assert np.array_equal(a.us, c.us) and np.array_equal(a.xs, c.xs) and np.array_equal(a.qp_count, c.qp_count)
+    assert np.array_equal(b.us, a.us[1500:1700]) and np.array_equal(b.xs, a.xs[1500:1700])
+    assert np.array_equal(b.counters, a.counters[1500:1700])
