@@ -1,8 +1,16 @@
 """Surrogate-model containers -- API of mpc4quantum/model.py.
 
-Only the read-only container ``DMDc`` (model.py:7-103) is on the MPC hot path.  The data-driven fitting classes
-(``DiscrepDMDc`` model.py:109-213, ``OnlineDMDc`` model.py:216-313) are reached only through
-``mpc(streaming=True)``; their names exist so that scripts import cleanly, fitting raises NotImplementedError.
+``DMDc`` (model.py:7-103) is the read-only container on the MPC hot path: ``get_discrete()`` hands the blocks
+``[A_x | A_u]`` to the device once, when the closed-loop plan is built.
+
+``DiscrepDMDc`` (model.py:109-213) and ``OnlineDMDc`` (model.py:216-313) are the data-driven variants that
+``mpc(streaming=True)`` updates after every MPC step (mpc.py:281-285).  They are small dense host-side updates
+(one pseudo-inverse, or one rank-1 recursive-least-squares step, per MPC step) and run in numpy.
+
+Reference behaviour kept on purpose: both ``fit_iteration`` implementations REBIND ``self.A`` to a new array.  The
+controller inside ``mpc()`` linearises through operators captured before the loop (mpc.py:156, linearize.py:13-32),
+so a streaming run keeps controlling with the model it started from; the updates are visible to ``model.predict``
+(the steps between plant measurements, mpc.py:264-267) and in the model that ``mpc()`` returns.
 """
 import numpy as np
 
@@ -41,15 +49,119 @@ class DMDc:
         return self.A[:self.dim_y, :self.dim_x], self.A[:self.dim_y, self.dim_x:]
 
 
-class DiscrepDMDc(DMDc):
-    """Placeholder for model.py:109-213 (discrepancy DMDc); fitting is outside the accelerated path."""
+def _regressors(X, U):
+    """Z = [X; U] and dim_u for an optional control block."""
+    if U is None:
+        return X, 0
+    return np.vstack([X, U]), U.shape[0]
 
-    def fit_iteration(self, next_y, next_x, next_u):
-        raise NotImplementedError('streaming model updates are not part of the B200 hot path yet')
+
+class _History:
+    """Optional in-memory history of the fitted operators, every `_isave` iterations (model.py:131-135, 235-239)."""
+
+    def _init_history(self):
+        self._save = False
+        self._iteration = 0
+        self._isave = 10
+
+    def _tick(self):
+        self._iteration += 1
+        return self._save and self._iteration % self._isave == 0
 
 
-class OnlineDMDc(DMDc):
-    """Placeholder for model.py:216-313 (recursive least squares DMDc); fitting is outside the accelerated path."""
+class DiscrepDMDc(DMDc, _History):
+    """Discrepancy DMDc (model.py:109-213): keeps (discounted) snapshot stacks and, once the state stack has rank
+    `min_rank`, adds the least-squares fit of the current prediction error to the model."""
 
-    def fit_iteration(self, next_y, next_x, next_u):
-        raise NotImplementedError('streaming model updates are not part of the B200 hot path yet')
+    def __init__(self, dim_y, dim_x, dim_u, A0, **kwargs):
+        super().__init__(dim_y, dim_x, dim_u, A0)
+        self.initialization = kwargs
+        self.Y = kwargs.get('Y')
+        self.X = kwargs.get('X')
+        self.U = kwargs.get('U')
+        self.discount = kwargs.get('discount', self.discount)
+        self.rcond = kwargs.get('rcond', self.rcond)
+        self.min_rank = dim_x
+        self.iA = [A0]
+        self._init_history()
+
+    @classmethod
+    def from_randn(cls, dim_y, dim_x, dim_u, **kwargs):
+        """A0 ~ sigma * N(0, 1), real (global numpy RNG, as the reference: model.py:137-150)."""
+        sigma = kwargs['sigma']
+        return cls(dim_y, dim_x, dim_u, sigma * np.random.randn(dim_y, dim_x + dim_u), sigma=sigma)
+
+    @classmethod
+    def from_bootstrap(cls, dim_y, dim_x, dim_u, A0, **kwargs):
+        return cls(dim_y, dim_x, dim_u, A0)
+
+    @classmethod
+    def from_data(cls, Y, X, U=None, **kwargs):
+        """A0 = Y pinv([X; U], rcond) (model.py:157-178)."""
+        rcond = kwargs['rcond']
+        Z, dim_u = _regressors(X, U)
+        return cls(Y.shape[0], X.shape[0], dim_u, Y @ np.linalg.pinv(Z, rcond=rcond), Y=Y, X=X, U=U, rcond=rcond)
+
+    @staticmethod
+    def _update_stack(val, stack, discount, nadd=1):
+        cols = np.reshape(val, (-1, nadd))
+        return cols if stack is None else np.hstack([discount * stack, cols])
+
+    def fit_iteration(self, next_y, next_x, next_u=np.array([])):
+        self.Y = self._update_stack(next_y, self.Y, self.discount)
+        self.X = self._update_stack(next_x, self.X, self.discount)
+        self.U = self._update_stack(next_u, self.U, self.discount)
+        if np.linalg.matrix_rank(self.X) >= self.min_rank:
+            residual = self.Y - self.predict(self.X, self.U)
+            self.A = self.A + residual @ np.linalg.pinv(np.vstack([self.X, self.U]), rcond=self.rcond)
+        if self._tick():
+            self.iA.append(np.copy(self.A))
+        return self.get_discrete()
+
+    def append(self, Y, X, U):
+        n = Y.shape[1]
+        self.Y = self._update_stack(Y, self.Y, 1, n)
+        self.X = self._update_stack(X, self.X, 1, n)
+        self.U = self._update_stack(U, self.U, 1, n)
+
+
+class OnlineDMDc(DMDc, _History):
+    """Recursive-least-squares DMDc (model.py:216-313; Zhang et al., online DMD): with z = [x; u],
+    gamma = 1 / (1 + z^T P z),  A += gamma (y - A z) (P z)^T,  P = (P - gamma (P z)(P z)^T) / discount.
+    The products use the plain transpose, also for complex data, as the reference does (model.py:300-305)."""
+
+    def __init__(self, dim_y, dim_x, dim_u, P0, A0, **kwargs):
+        super().__init__(dim_y, dim_x, dim_u, A0)
+        self.initialization = kwargs
+        self.P = P0
+        self.iP = [P0]
+        self.iA = [A0]
+        self._init_history()
+
+    @classmethod
+    def from_randn(cls, dim_y, dim_x, dim_u, **kwargs):
+        dim_z = dim_x + dim_u
+        P0 = kwargs['alpha'] * np.identity(dim_z)
+        return cls(dim_y, dim_x, dim_u, P0, kwargs['sigma'] * np.random.randn(dim_y, dim_z), **kwargs)
+
+    @classmethod
+    def from_bootstrap(cls, dim_y, dim_x, dim_u, A0, **kwargs):
+        return cls(dim_y, dim_x, dim_u, kwargs['alpha'] * np.identity(dim_x + dim_u), A0, **kwargs)
+
+    @classmethod
+    def from_data(cls, Y, X, U=None, **kwargs):
+        Z, dim_u = _regressors(X, U)
+        P0 = np.linalg.pinv(Z @ Z.T)
+        return cls(Y.shape[0], X.shape[0], dim_u, P0, Y @ Z.T @ P0, Y=Y, X=X, U=U)
+
+    def fit_iteration(self, next_y, next_x, next_u=np.array([])):
+        y = np.reshape(next_y, (-1, 1))
+        z = np.vstack([np.reshape(next_x, (-1, 1)), np.reshape(next_u, (-1, 1))])
+        Pz = self.P @ z
+        gamma = 1 / (1 + z.T @ Pz)
+        self.A = self.A + gamma * (y - self.A @ z) @ Pz.T
+        self.P = (self.P - gamma * Pz @ Pz.T) / self.discount
+        if self._tick():
+            self.iA.append(np.copy(self.A))
+            self.iP.append(np.copy(self.P))
+        return self.get_discrete()

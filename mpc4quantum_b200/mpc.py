@@ -273,16 +273,14 @@ def mpc(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sa
 
     exit codes: 0 normal, 1 exit_condition met, 2 QP not certified, 3 non-finite QP (mpc.py:131, :195, :202, :291).
     """
-    if streaming:
-        raise NotImplementedError('streaming model updates (mpc.py:281-285) are not part of the B200 hot path yet')
     if sat is None:
         raise TypeError('sat is mandatory: the reference fails at optimize.py:43 without it')
     x0 = np.asarray(x0, dtype=complex).reshape(-1)
-    if _device_plant(experiment) and exit_condition is None:
+    if _device_plant(experiment) and exit_condition is None and not streaming:
         return _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,
                           warm_start)
     return _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,
-                             exit_condition, warm_start)
+                             exit_condition, warm_start, streaming)
 
 
 def _finish(xs, us, steps_done, exit_code, clock, model):
@@ -312,9 +310,15 @@ def _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R,
 
 
 def _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,
-                      exit_condition, warm_start):
-    """User-defined plant / exit condition: the iterative QP of each step runs on the device (one launch per MPC
-    step, guesses and ADMM state stay resident), the plant and the callbacks run on the host (mpc.py:247-292)."""
+                      exit_condition, warm_start, streaming=False):
+    """User-defined plant / exit condition / streaming model: the iterative QP of each step runs on the device (one
+    launch per MPC step, guesses and ADMM state stay resident), the plant, the callbacks and the model update run on
+    the host (mpc.py:247-292).
+
+    streaming (mpc.py:281-285): ``model.fit_iteration`` is called after every step with the lifted transition.  As in
+    the reference, the controller keeps linearising the operators it captured before the loop (mpc.py:156 wraps
+    views that ``fit_iteration`` never writes through: it rebinds ``model.A``), so the device blocks are NOT
+    re-uploaded; the updated model acts through ``model.predict`` and is returned to the caller."""
     from scipy.interpolate import interp1d
     c = model.get_discrete()[0].shape[1]
     plan = ClosedLoopPlan(dim_u, order, X_targ, U_targ, clock, model, Q, R, Qf, sat, du, d=0, max_iter=max_iter,
@@ -343,6 +347,11 @@ def _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model
             lift_u = wrapped.lift_u(us[step].reshape(-1, 1))
             lift_x = np.asarray(experiment.lift(xs[step])).reshape(-1, 1)
             xs[step + 1] = np.asarray(experiment.proj(model.predict(lift_x, krtimes(lift_u, lift_x)))).flatten()
+        if streaming:
+            lift_ustep = wrapped.lift_u(us[step].reshape(-1, 1))
+            lift_xstep = np.asarray(experiment.lift(xs[step])).reshape(-1, 1)
+            model.fit_iteration(np.asarray(experiment.lift(xs[step + 1])).reshape(-1, 1), lift_xstep,
+                                krtimes(lift_ustep, lift_xstep))
         if exit_condition is not None and exit_condition(xs[step + 1], xs[step], us[step]):
             exit_code = 1
             step += 1

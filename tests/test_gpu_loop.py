@@ -283,3 +283,23 @@ def test_transmon_bitwise_repeatable_across_batch_compositions():
     assert np.array_equal(a.us, c.us) and np.array_equal(a.xs, c.xs) and np.array_equal(a.qp_count, c.qp_count)
     assert np.array_equal(b.us, a.us[1500:1700]) and np.array_equal(b.xs, a.xs[1500:1700])
     assert np.array_equal(b.counters, a.counters[1500:1700])
+
+
+def test_streaming_model_updates_match_the_reference_loop():
+    """mpc(streaming=True) (mpc.py:281-285) with an OnlineDMDc model, against the reference's own loop (fixture from
+    oracle/make_golden_streaming.py): same controls, states and the same updated model; the model that comes back has
+    moved, the controller kept the operators it started with (reference behaviour, see model.py docstring)."""
+    g = load_golden('streaming')
+    cfg = systems.config_qubit_freq(1, n_steps=15)
+    assert np.abs(cfg['model'].A - g['loop_A0']).max() < 1e-13
+    c = 4
+    model = m4q.OnlineDMDc.from_bootstrap(c, c, cfg['model'].A.shape[1] - c, cfg['model'].A.copy(), alpha=1e2)
+    args, kw = systems.mpc_args(cfg)
+    args = list(args)
+    args[7] = model
+    (xs, us), model2, ec = m4q.mpc(*args, streaming=True, **kw)
+    assert ec == 0 and model2 is model
+    assert np.abs(us - g['loop_us']).max() < U_TOL, np.abs(us - g['loop_us']).max()
+    assert np.abs(xs - g['loop_xs']).max() < 10 * U_TOL
+    assert np.abs(model.A - g['loop_A']).max() < 1e-4 and np.abs(model.P - g['loop_P']).max() < 1e-2
+    assert np.abs(model.A - g['loop_A0']).max() > 1e-2

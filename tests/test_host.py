@@ -129,7 +129,43 @@ def test_dmdc_container_and_lifts(unit_golden):
     assert np.allclose(m4q.QExperiment32.lift(rho3), np.diag([2 / 3, 1 / 3]).reshape(-1))
     assert m4q.isqrt(16) == 4
     with pytest.raises(NotImplementedError):
-        m4q.OnlineDMDc(2, 4, 8, A).fit_iteration(None, None, None)
+        m4q.DMDc(2, 4, 8, A).fit_iteration(None, None, None)      # read-only container (model.py:70-79)
+
+
+def test_online_and_discrepancy_dmdc_match_the_reference():
+    """model.py:109-313 against vectors produced by the reference's own classes (oracle/make_golden_streaming.py)."""
+    from conftest import load_golden
+    g = load_golden('streaming')
+    dy, dx, du = 4, 4, 8
+    mdl = m4q.OnlineDMDc.from_bootstrap(dy, dx, du, g['on_A0'].copy(), alpha=1e2)
+    mdl.discount = 0.95
+    A_first = mdl.A
+    for k in range(6):
+        A_x, A_u = mdl.fit_iteration(g['on_y'][k], g['on_x'][k], g['on_u'][k])
+    assert np.abs(mdl.A - g['on_A']).max() < 1e-12 and np.abs(mdl.P - g['on_P']).max() < 1e-10
+    assert A_x.shape == (dy, dx) and A_u.shape == (dy, du) and np.array_equal(np.hstack([A_x, A_u]), mdl.A)
+    assert mdl.A is not A_first and np.array_equal(A_first, g['on_A0'])   # rebinding, not in place (see mpc streaming)
+    assert np.abs(mdl.predict(g['on_x'][0], g['on_u'][0]) - g['on_pred']).max() < 1e-12
+    mdl = m4q.OnlineDMDc.from_data(g['on_Y'], g['on_X'], g['on_U'])
+    mdl.fit_iteration(g['on_y'][0], g['on_x'][0], g['on_u'][0])
+    assert np.abs(mdl.A - g['on_data_A']).max() < 1e-10 and np.abs(mdl.P - g['on_data_P']).max() < 1e-10
+
+    mdl = m4q.DiscrepDMDc.from_data(g['on_Y'], g['on_X'], g['on_U'], rcond=1e-8)
+    assert np.abs(mdl.A - g['di_A0']).max() < 1e-12
+    mdl.discount = 0.9
+    for k in range(3):
+        mdl.fit_iteration(g['on_y'][k], g['on_x'][k], g['on_u'][k])
+    assert np.abs(mdl.A - g['di_A']).max() < 1e-10 and np.abs(mdl.Y - g['di_Ystack']).max() < 1e-13
+    mdl = m4q.DiscrepDMDc.from_bootstrap(dy, dx, du, g['on_A0'].copy())
+    for k in range(2):
+        mdl.fit_iteration(g['on_y'][k], g['on_x'][k], g['on_u'][k])
+    assert np.array_equal(mdl.A, g['di_boot_A_rank_deficient']) and np.array_equal(mdl.A, g['on_A0'])   # rank < dim_x
+    for k in range(2, 6):
+        mdl.fit_iteration(g['on_y'][k], g['on_x'][k], g['on_u'][k])
+    assert np.abs(mdl.A - g['di_boot_A']).max() < 1e-9
+    mdl._save, mdl._isave = True, 1
+    mdl.fit_iteration(g['on_y'][0], g['on_x'][0], g['on_u'][0])
+    assert len(mdl.iA) == 2
 
 
 def test_ensemble_draws_are_reproducible_and_shardable():
