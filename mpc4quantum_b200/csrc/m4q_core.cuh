@@ -697,7 +697,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     }
     // q_t per lane: Qbar_t r_t (table, register-prefetched) for the Riccati modes; the adjoint takes
     // -2 Qbar_t (x_t - r_t) (diagonal Qbar) from the record, where the last rollout left x_t - r_t
-    double p = 0.0, dv_n = 0.0, ql_n = 0.0, gmax = 0.0;
+    double p = 0.0, dv_n = 0.0, ql_n = 0.0;
     if (act) {
         p = adj ? 2.0 * qp.Qf[lane * N + lane] * s.xT[lane] : -qp.qlinf[lane];
         if (!adj) {
@@ -744,7 +744,6 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             g[i] = mk[i] ? 0.0 : g[i] - hv[i];
-            if (adj) gmax = fmax(gmax, fabs(g[i]));
         }
         double pn = atv - ql;
         if (lane < M) {
@@ -758,10 +757,16 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         p = pn;
     }
     __syncwarp();   // kk complete; va/vb free again
-    if (adj) return gmax;
+    if (adj) {      // max |grad| over the horizon
+        double gm = 0.0;
+#pragma unroll 1
+        for (int e = lane; e < H * M; e += 32) gm = fmax(gm, fabs(s.kk[e]));
+        return warp_max(gm);
+    }
     // forward: record 0 is still in slot 0
     double x = act ? s.x0[lane] : 0.0;
     if (WRITE_X && act) Xo[lane] = x;
+    double r_n = (WRITE_X && act) ? qp.r[lane] : 0.0;   // target of the stage, register-prefetched one stage ahead
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const double *slot = rec_slot<CF>(s, t);
@@ -769,7 +774,10 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) {
             vec[lane] = x;
-            if (WRITE_X) ws_rec<CF>(sr, t)[R_::XC + lane] = x - qp.r[t * N + lane];
+            if (WRITE_X) {
+                ws_rec<CF>(sr, t)[R_::XC + lane] = x - r_n;
+                r_n = qp.r[(t + 1) * N + lane];
+            }
         }
         cp_async_wait_all();
         __syncwarp();
@@ -810,7 +818,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
     }
-    if (act) s.xT[lane] = x - qp.r[H * N + lane];
+    if (act) s.xT[lane] = x - (WRITE_X ? r_n : qp.r[H * N + lane]);
     __syncwarp();
     // a non-finite state anywhere in the rollout propagates to x_H
     return __any_sync(FULL, !isfinite(x)) ? 1.0 : 0.0;
