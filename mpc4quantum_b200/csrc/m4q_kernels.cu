@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 template <class CF> __host__ __device__ inline long long qp_ws_doubles(int H) {
     constexpr int N = CF::N, M = CF::M;
-    return (long long)(H + 1) * N * N + (long long)H * M * M + 2LL * (H + 1) * N + 2LL * rup(H * M, 2) + ws_doubles<CF>(H);
+    // every block starts on a 16-byte boundary (the stage records behind it are moved with 16-byte cp.async)
+    return (long long)(H + 1) * N * N + rup(H * M * M, 2) + 2LL * (H + 1) * N + 2LL * rup(H * M, 2) + ws_doubles<CF>(H);
 }
 
 struct QpArgs {
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
 
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         double *ws = a.ws + k * qp_ws_doubles<CF>(H);
-        double *wQ = ws, *wR = wQ + (size_t)(H + 1) * N * N, *wr = wR + H * M * M, *wql = wr + (H + 1) * N,
+        double *wQ = ws, *wR = wQ + (size_t)(H + 1) * N * N, *wr = wR + rup(H * M * M, 2), *wql = wr + (H + 1) * N,
                *wub = wql + (H + 1) * N, *wRub = wub + rup(H * M, 2);
         sr.ws = wRub + rup(H * M, 2);
         const double2 *Qk = a.Q_ls + (size_t)k * (H + 1) * C * C;

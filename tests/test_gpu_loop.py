@@ -303,3 +303,17 @@ def test_streaming_model_updates_match_the_reference_loop():
     assert np.abs(xs - g['loop_xs']).max() < 10 * U_TOL
     assert np.abs(model.A - g['loop_A']).max() < 1e-4 and np.abs(model.P - g['loop_P']).max() < 1e-2
     assert np.abs(model.A - g['loop_A0']).max() > 1e-2
+
+
+@pytest.mark.parametrize('maker,H', [(lambda H: systems.config_transmon(1, horizon=H, n_steps=5), 9),
+                                     (lambda H: systems.config_transmon(2, horizon=H, n_steps=4), 7),
+                                     (lambda H: systems.config_cnot(n_steps=3, horizon=H, ramp_steps=50), 5)])
+def test_odd_horizons_match_oracle(maker, H):
+    """Odd horizons exercise the 16-byte alignment of every per-stage array (records, rings, control vectors)."""
+    cfg = maker(H)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    xs_c, us_c, ec_c, stats = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list)
+    assert ec == 0 == ec_c
+    assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
+    assert np.abs(xs - xs_c).max() < 10 * U_TOL

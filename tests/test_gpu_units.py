@@ -127,3 +127,61 @@ def test_sat_is_mandatory(qp_golden):
     with pytest.raises(TypeError):
         optimize.quad_program(g['qubit_x_init'][0], g['qubit_X_bm'][0], g['qubit_U_bm'][0], [g['qubit_Q']] * 11,
                               [g['qubit_R']] * 10, list(g['qubit_A'][0]), list(g['qubit_B'][0]), list(g['qubit_D'][0]))
+
+
+def _random_qp(rng, c, m, H, hermitian_cost, with_du):
+    """A random instance of the QP of optimize.py:12-60: near-unitary time-varying dynamics, general affine term,
+    targets that force part of the controls onto their bounds."""
+    def crandn(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    A_ls, B_ls, D_ls = [], [], []
+    for _ in range(H):
+        K = crandn(c, c)
+        A_ls.append(np.eye(c) + 0.15 * (K - K.conj().T) / np.sqrt(c) + 0.01 * crandn(c, c) / np.sqrt(c))
+        B_ls.append(0.4 * crandn(c, m))
+        D_ls.append(0.05 * crandn(c, 1))
+    if hermitian_cost:
+        L = crandn(c, c) / np.sqrt(c)
+        Q = L @ L.conj().T
+        Lf = crandn(c, c) / np.sqrt(c)
+        Qf = Lf @ Lf.conj().T
+        Lr = rng.standard_normal((m, m))
+        R = 0.05 * (Lr @ Lr.T + np.eye(m))
+    else:
+        Q = np.diag(rng.uniform(0.0, 1.0, c)).astype(complex)
+        Qf = 2.0 * Q
+        R = np.diag(rng.uniform(0.02, 0.1, m))
+    x_init = crandn(c)
+    X_bm = crandn(c, H + 1)
+    U_bm = 0.3 * rng.standard_normal((m, H))
+    sat = 0.6
+    du = 0.25 if with_du else None
+    u_prev = 0.3 * rng.standard_normal(m)
+    return (x_init, X_bm, U_bm, [Q] * H + [Qf], [R] * H, A_ls, B_ls, D_ls, u_prev, sat, du)
+
+
+@pytest.mark.parametrize('c,m', [(4, 1), (4, 2), (8, 2), (9, 2), (16, 3)])
+def test_quad_program_random_instances_all_instantiations(c, m):
+    """Every compiled (dim_x, dim_u) kernel against the exact oracle on random QPs: diagonal and full Hermitian costs,
+    with and without the rate bound, short and medium horizons.  Tight mode: controls within 1e-8."""
+    from oracle import restate as rs
+    rng = np.random.default_rng(1000 * c + m)
+    worst = 0.0
+    for H in (3, 8, 20):
+        for hermitian_cost in (False, True):
+            for with_du in (True, False):
+                a = _random_qp(rng, c, m, H, hermitian_cost, with_du)
+                Xc, Uc, objc, info = rs.qp_exact(*a)
+                assert max(info['kkt']) < 1e-7
+                X, U, obj, qinfo = optimize.quad_program(*a)
+                assert qinfo.status_code == 0, (c, m, H, hermitian_cost, with_du)
+                err = np.abs(U - Uc).max()
+                worst = max(worst, err)
+                assert err < 1e-8, (c, m, H, hermitian_cost, with_du, err)
+                assert np.abs(X - Xc).max() < 1e-7
+                assert abs(obj - objc) < 1e-8 * max(1.0, abs(objc))
+                lo, hi = rs.qp_bounds(a[2], a[8], a[9], a[10])
+                assert (U >= lo - 1e-12).all() and (U <= hi + 1e-12).all()
+                n_active = int((np.abs(Uc - lo) < 1e-9).sum() + (np.abs(Uc - hi) < 1e-9).sum())
+                assert 0 <= n_active <= U.size
+    assert worst < 1e-8
