@@ -317,3 +317,22 @@ def test_odd_horizons_match_oracle(maker, H):
     assert ec == 0 == ec_c
     assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
     assert np.abs(xs - xs_c).max() < 10 * U_TOL
+
+
+def test_full_hermitian_costs_take_the_general_paths():
+    """Every BASELINE config has diagonal Q and R; a full Hermitian Q / symmetric R sends the fused kernel through the
+    general adjoint-gradient sweep and the block-by-block line search (mpc.py:103-107 with a dense metric)."""
+    cfg = systems.config_transmon(1, horizon=10, n_steps=6)
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((9, 9)) + 1j * rng.standard_normal((9, 9))
+    V, _ = np.linalg.qr(G)
+    Q = V @ np.diag([1.0, 0.5, 0, 0, 1.0, 0, 0.2, 0, 0]) @ V.conj().T
+    Q = 0.5 * (Q + Q.conj().T) + cfg['Q']
+    R = cfg['R'] * np.array([[1.0, 0.3], [0.3, 1.5]])
+    cfg['Q'], cfg['Qf'], cfg['R'] = Q, 2.0 * Q, R
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    xs_c, us_c, ec_c, stats = _oracle_loop(cfg, cfg['experiment'].H0, cfg['experiment'].H1_list)
+    assert ec == 0 == ec_c
+    assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
+    assert np.abs(xs - xs_c).max() < 10 * U_TOL
