@@ -336,3 +336,27 @@ def test_full_hermitian_costs_take_the_general_paths():
     assert ec == 0 == ec_c
     assert np.abs(us - us_c).max() < U_TOL, np.abs(us - us_c).max()
     assert np.abs(xs - xs_c).max() < 10 * U_TOL
+
+
+def test_device_exit_condition_retires_members_independently():
+    """Built-in exit condition (mpc.py:289-292 as a device predicate): a member stops with exit code 1 as soon as its
+    infidelity drops below the threshold; the steps it did take equal the unconditioned run, the others go on."""
+    cfg = systems.config_transmon(1)
+    ens, _ = systems.ensemble_transmon(65536)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    sub = ens.slice(0, 128)
+    full = m4q.mpc_ensemble(args[0], *args[1:6], sub, *args[7:], fid_target=cfg['target'], **kw)
+    thr = 5e-3
+    early = m4q.mpc_ensemble(args[0], *args[1:6], sub, *args[7:], fid_target=cfg['target'], exit_infidelity=thr, **kw)
+    S = cfg['clock'].n_steps
+    stopped = early.exit_code == 1
+    assert stopped.any() and (early.exit_code[~stopped] == 0).all()
+    assert (early.steps_done[~stopped] == S).all() and (early.steps_done[stopped] < S).all()
+    fid_traj = np.real(np.einsum('i,nis->ns', np.conj(cfg['target']), full.xs))       # <target|rho_s|target>
+    for k in np.flatnonzero(stopped)[:16]:
+        n = int(early.steps_done[k])
+        # steps_done counts completed steps; the state after the last one is the first below the threshold
+        assert 1.0 - fid_traj[k, n] < thr and (1.0 - fid_traj[k, 1:n] >= thr).all()
+        assert np.array_equal(early.us[k, :, :n], full.us[k, :, :n])
+        assert np.array_equal(early.xs[k, :, :n + 1], full.xs[k, :, :n + 1])
