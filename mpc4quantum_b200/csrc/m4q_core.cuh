@@ -35,7 +35,7 @@ __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };
 template <> struct Tiles<9, 2> { static constexpr int MAXW = 12; };   // 3 warps per scheduler: 168 registers, no spills
-template <> struct Tiles<8, 2> { static constexpr int MAXW = 12; };    // same register argument as <9, 2>
+template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };
 template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
 
 template <int C_, int M_> struct Cfg {
