@@ -1,9 +1,12 @@
-// Warp-level building blocks of the MPC hot path (sm_100a).  One warp owns one ensemble member; all per-member
-// state lives in a warp-private slab of shared memory, the model blocks / costs are CTA-shared and read-only.
+// Warp-level building blocks of the MPC hot path (sm_100a).  One warp owns one ensemble member.  Its Riccati scratch,
+// control trajectories and staging rings live in a warp-private slab of shared memory; the horizon-length data
+// (stage records, state trajectories) live in an L2-resident workspace and are streamed through the slab with
+// cp.async; the model blocks / costs are CTA-shared and read-only.  DESIGN.md section 2 has the full picture.
 //
 // Reference semantics restated here (paths relative to the reference repository):
-//   linearize      mpc4quantum/linearize.py:37-70   (A_t never materialised: A_t = sum_k phi_k(u_t) * block_k)
-//   QP             mpc4quantum/optimize.py:12-60    (ADMM on the control box, Riccati inner solve, active-set polish)
+//   linearize      mpc4quantum/linearize.py:37-70   (A_t = sum_k phi_k(u_t) * block_k, formed once per stage)
+//   QP             mpc4quantum/optimize.py:12-60    (warm active set / ADMM on the control box, Riccati inner solve
+//                                                     on the fp64 tensor cores, KKT certificate)
 //   line search    mpc4quantum/mpc.py:101-125       (time-major metric paired with state-major vectors)
 //   plant          mpc4quantum/experiment.py:202-212 + mpc.py:256-260 (expm conjugation per segment)
 //   lift / proj    mpc4quantum/experiment.py:29-37, 225-235, 248-306
@@ -33,9 +36,9 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r - x % m) % m + m) % m; }
 __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };
+template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };   // 128 registers
 template <> struct Tiles<9, 2> { static constexpr int MAXW = 12; };   // 3 warps per scheduler: 168 registers, no spills
-template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };
+template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };   // 15 fit; measured faster than 12 x 168 registers
 template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
 
 template <int C_, int M_> struct Cfg {
