@@ -456,16 +456,18 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll
             for (int q = 0; q < NE; ++q) ar[q] = ai[q] = 0.0;
             const double2 *bp = blk0 + lane;
+            // loads of one block issued together (NE independent 16-byte loads), clamped instead of predicated
+            const int qlast = (C * C - 1 - lane) >> 5;   // last valid q of this lane
 #pragma unroll 1
             for (int kb = 0; kb < ops.nblk; ++kb, bp += C * C) {
                 const double ph = phi_t[kb];
+                double2 v[NE];
+#pragma unroll
+                for (int q = 0; q < NE; ++q) v[q] = bp[32 * (q < qlast ? q : qlast)];
 #pragma unroll
                 for (int q = 0; q < NE; ++q) {
-                    if (lane + 32 * q < C * C) {
-                        const double2 v = bp[32 * q];
-                        ar[q] = fma(ph, v.x, ar[q]);
-                        ai[q] = fma(ph, v.y, ai[q]);
-                    }
+                    ar[q] = fma(ph, v[q].x, ar[q]);
+                    ai[q] = fma(ph, v[q].y, ai[q]);
                 }
             }
 #pragma unroll
