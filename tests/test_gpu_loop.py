@@ -360,3 +360,37 @@ def test_device_exit_condition_retires_members_independently():
         assert 1.0 - fid_traj[k, n] < thr and (1.0 - fid_traj[k, 1:n] >= thr).all()
         assert np.array_equal(early.us[k, :, :n], full.us[k, :, :n])
         assert np.array_equal(early.xs[k, :, :n + 1], full.xs[k, :, :n + 1])
+
+
+def test_per_member_initial_states_and_shared_hamiltonian():
+    """Ensemble axes other than the plant: per-member x0 (x0 [N, d*d]) and, at the C ABI, one shared Hamiltonian."""
+    from oracle import restate as rs
+    cfg = systems.config_qubit(1)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    rng = np.random.default_rng(11)
+    n = 40
+    x0s = []
+    for _ in range(n):
+        th, ph = rng.uniform(0, 0.6), rng.uniform(0, 2 * np.pi)
+        psi = np.array([np.cos(th / 2), np.exp(1j * ph) * np.sin(th / 2)])
+        x0s.append(np.outer(psi, psi.conj()).reshape(-1))
+    x0s = np.array(x0s)
+    ex = cfg['experiment']
+    ens = m4q.EnsembleQExperiment(np.repeat(ex.H0[None], n, axis=0), np.repeat(np.stack(ex.H1_list)[None], n, axis=0))
+    res = m4q.mpc_ensemble(x0s, *args[1:6], ens, *args[7:], fid_target=cfg['target'], **kw)
+    assert (res.exit_code == 0).all()
+    assert np.abs(res.xs[:, :, 0] - x0s).max() == 0
+    for k in (0, 7, 39):
+        c2 = dict(cfg)
+        c2['x0'] = x0s[k]
+        xs_c, us_c, ec_c, _ = _oracle_loop(c2, ex.H0, ex.H1_list)
+        assert ec_c == 0 and np.abs(res.us[k] - us_c).max() < U_TOL and np.abs(res.xs[k] - xs_c).max() < 10 * U_TOL
+    # one Hamiltonian for everybody through ClosedLoopPlan.run(shared_hamiltonian=True)
+    from mpc4quantum_b200 import _lib
+    from mpc4quantum_b200.mpc import ClosedLoopPlan
+    plan = ClosedLoopPlan(cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'], cfg['model'], cfg['Q'],
+                          cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], 2, ex.lift_mode, 100, cfg['warm_start'], capacity=n)
+    out = plan.run(_lib.dev(x0s, np.complex128), _lib.dev(ex.H0[None], np.complex128),
+                   _lib.dev(np.stack(ex.H1_list)[None], np.complex128), n=n, shared_hamiltonian=True).numpy()
+    assert np.array_equal(out.us, res.us) and np.array_equal(out.xs, res.xs)
