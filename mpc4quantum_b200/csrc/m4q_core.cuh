@@ -511,17 +511,30 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 for (int ni = 0; ni < QT; ++ni) w[mi][ni][0] = w[mi][ni][1] = 0.0;
             const double *pa = s.P + g8 * LDP + c4;      // A fragment: P[mi*8 + g8][ks*4 + c4]
             const double *gb = s.AB + c4 * LDG + g8;     // B fragment: G[ks*4 + c4][ni*8 + g8]
+            // software pipelined: the fragments of k-step ks + 1 are in flight while the MMAs of ks issue
+            double af[MT], bf[QT];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) af[mi] = pa[mi * 8 * LDP];
+#pragma unroll
+            for (int ni = 0; ni < QT; ++ni) bf[ni] = gb[ni * 8];
 #pragma unroll 1
-            for (int ks = 0; ks < KS; ++ks, pa += 4, gb += 4 * LDG) {
-                double af[MT], bf[QT];
+            for (int ks = 0; ks < KS; ++ks) {
+                double an[MT], bn[QT];
+                const int adv = ks + 1 < KS ? 1 : 0;   // the last step re-loads its own fragments (no branch)
+                pa += 4 * adv;
+                gb += 4 * LDG * adv;
 #pragma unroll
-                for (int mi = 0; mi < MT; ++mi) af[mi] = pa[mi * 8 * LDP];
+                for (int mi = 0; mi < MT; ++mi) an[mi] = pa[mi * 8 * LDP];
 #pragma unroll
-                for (int ni = 0; ni < QT; ++ni) bf[ni] = gb[ni * 8];
+                for (int ni = 0; ni < QT; ++ni) bn[ni] = gb[ni * 8];
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < QT; ++ni) dmma(w[mi][ni], af[mi], bf[ni]);
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) af[mi] = an[mi];
+#pragma unroll
+                for (int ni = 0; ni < QT; ++ni) bf[ni] = bn[ni];
             }
             double2 *wd = reinterpret_cast<double2 *>(s.W + g8 * LDG + 2 * c4);
 #pragma unroll
@@ -542,17 +555,29 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                 for (int ni = mi; ni < QT; ++ni) tt[mi][ni][0] = tt[mi][ni][1] = 0.0;
             const double *ga = s.AB + c4 * LDG + g8;     // A fragment: G^T[mi*8 + g8][ks*4 + c4] = G[ks*4 + c4][mi*8 + g8]
             const double *wb = s.W + c4 * LDG + g8;      // B fragment: W[ks*4 + c4][ni*8 + g8]
+            double af[QT], bf[QT];
+#pragma unroll
+            for (int mi = 0; mi < QT; ++mi) af[mi] = ga[mi * 8];
+#pragma unroll
+            for (int ni = 0; ni < QT; ++ni) bf[ni] = wb[ni * 8];
 #pragma unroll 1
-            for (int ks = 0; ks < KS; ++ks, ga += 4 * LDG, wb += 4 * LDG) {
-                double af[QT], bf[QT];
+            for (int ks = 0; ks < KS; ++ks) {
+                double an[QT], bn[QT];
+                const int adv = ks + 1 < KS ? 4 * LDG : 0;
+                ga += adv;
+                wb += adv;
 #pragma unroll
-                for (int mi = 0; mi < QT; ++mi) af[mi] = ga[mi * 8];
+                for (int mi = 0; mi < QT; ++mi) an[mi] = ga[mi * 8];
 #pragma unroll
-                for (int ni = 0; ni < QT; ++ni) bf[ni] = wb[ni * 8];
+                for (int ni = 0; ni < QT; ++ni) bn[ni] = wb[ni * 8];
 #pragma unroll
                 for (int mi = 0; mi < QT; ++mi)
 #pragma unroll
                     for (int ni = mi; ni < QT; ++ni) dmma(tt[mi][ni], af[mi], bf[ni]);
+#pragma unroll
+                for (int mi = 0; mi < QT; ++mi) af[mi] = an[mi];
+#pragma unroll
+                for (int ni = 0; ni < QT; ++ni) bf[ni] = bn[ni];
             }
             // publish, branch free: elements outside T11 / T12 / T22 go to a dummy slot (va is unused in the factor)
 #pragma unroll
