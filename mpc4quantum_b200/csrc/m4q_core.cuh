@@ -935,7 +935,8 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
 //   * primal-dual active set ("polish"): controls in the working set are pinned to their bound and folded into
 //     the dynamics, one masked Riccati factor + solve gives the equality-constrained optimum, and an adjoint
 //     gradient certifies the KKT conditions (multiplier signs on pinned controls, feasibility of free ones) or
-//     updates the set.
+//     updates the set.  The certificate is a full KKT check: stationarity of the free controls (1e-6 relative),
+//     primal feasibility (1e-12), multiplier signs (1e-10 relative).
 // Tight mode (polish = 1): the working set is warm-started from the previous solve's (z, y) -- the previous SQP
 // iterate or the shifted previous MPC step -- and the active-set rounds run first; an ADMM block (which needs no
 // guess) is the fallback that re-seeds the set when the rounds do not certify.  admm_first = 1 always runs the ADMM
@@ -1034,7 +1035,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             const double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
                                            : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             const double gs = fmax(1.0, gmax);
-            bool changed = false;
+            bool changed = false, unstationary = false;
 #pragma unroll 1
             for (int e = lane; e < HM; e += 32) {
                 const int t = e / M, i = e % M;
@@ -1045,6 +1046,9 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 if (mk == 0) {
                     if (u < lo - 1e-12) nm = 1;
                     else if (u > hi + 1e-12) nm = 2;
+                    // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
+                    // cost-to-go has outgrown fp64 (long horizons with the order-1 model)
+                    unstationary |= !(fabs(g) <= 1e-6 * gs);
                 } else if (mk == 1) {
                     if (g < -1e-10 * gs) nm = 0;
                 } else {
@@ -1057,7 +1061,9 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             }
             __syncwarp();
             if (!__any_sync(FULL, changed)) {
-                certified = true;
+                // same working set again: either it is certified, or the solve itself is not accurate enough and more
+                // rounds would repeat it -- hand over to the ADMM fallback (and, in the end, exit code 2)
+                certified = !__any_sync(FULL, unstationary);
                 break;
             }
         }
