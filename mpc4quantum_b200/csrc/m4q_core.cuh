@@ -677,14 +677,17 @@ __device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef 
 //   SWEEP_ADJOINT backward only: adjoint gradient of the condensed cost at the last rollout -> kk, returns max |grad|
 //                 lam_H = 2 Qf (x_H - r_H);  grad_t = 2 R (u_t - ub_t) + B_t^T lam_{t+1};
 //                 lam_t = 2 Q (x_t - r_t) + A_t^T lam_{t+1}          (diagonal costs; else adjoint_gradient())
+//   SWEEP_REFINE  one step of iterative refinement of the polish solve: the correction (du, dx) that cancels the
+//                 gradient left in kk on the free controls (same factorisation, homogeneous dynamics, x0 = 0) is
+//                 ADDED to Uo, Xo and the records' x - r
 // All three are the recursion  v = dv + p;  g = B^T v - h;  p <- A^T v - q - K^T g  with different (dv, h, q, K).
 // A pre-pass folds the control-space terms into one array hl: the linear term h of a free control, the bound of a
 // pinned one.  Stage records arrive through the ring one stage ahead; the per-lane scalars needed before the
 // stage's only warp sync are register-prefetched.  Writes Uo and, if WRITE_X, Xo (workspace).
 // ---------------------------------------------------------------------------------------------------------
-enum { SWEEP_ADMM = 0, SWEEP_POLISH = 1, SWEEP_ADJOINT = 2 };
+enum { SWEEP_ADMM = 0, SWEEP_POLISH = 1, SWEEP_ADJOINT = 2, SWEEP_REFINE = 3 };
 
-template <class CF, bool FUSED>
+template <class CF, bool FUSED, bool REFINE = false>
 __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, double rho_half, int mode, bool WRITE_X,
                                              int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
@@ -693,7 +696,8 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const bool act = lane < N;
-    const bool adj = mode == SWEEP_ADJOINT;
+    // the refinement variant is a separate (cold) instantiation: the hot copy stays small for the instruction cache
+    const bool adj = !REFINE && mode == SWEEP_ADJOINT, refine = REFINE;
     double *Xo = ws_Xo<CF>(sr);
     prefetch_stage<CF>(s, sr, H - 1, lane);
 #pragma unroll 1
@@ -703,6 +707,8 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         double h;
         if (mode == SWEEP_ADMM) {
             h = qp.Rub[e] + rho_half * (s.z[e] - s.y[e]);
+        } else if (refine) {
+            h = s.mask[e] ? 0.0 : -0.5 * s.kk[e];   // cost term g^T du = -2 h^T du; a pinned control does not move
         } else if (adj) {
             h = 0.0;
 #pragma unroll
@@ -728,13 +734,14 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     // q_t per lane: Qbar_t r_t (table, register-prefetched) for the Riccati modes; the adjoint takes
     // -2 Qbar_t (x_t - r_t) (diagonal Qbar) from the record, where the last rollout left x_t - r_t
     double p = 0.0, dv_n = 0.0, ql_n = 0.0;
-    if (act) {
+    if (act && !refine) {
         p = adj ? 2.0 * qp.Qf[lane * N + lane] * s.xT[lane] : -qp.qlinf[lane];
         if (!adj) {
             dv_n = ws_rec<CF>(sr, H - 1)[R_::DV + lane];
             ql_n = qp.qlin[(H - 1) * N + lane];
         }
     }
+    if (REFINE) __syncwarp();   // hl has been derived from kk before the backward sweep overwrites kk
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *slot = rec_slot<CF>(s, t);
@@ -743,7 +750,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         const double v = dv_n + p;
         double ql = ql_n;
         if (act) vec[lane] = v;
-        if (t > 0 && act && !adj) {
+        if (t > 0 && act && !adj && !refine) {
             dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
             ql_n = qp.qlin[(t - 1) * N + lane];
         }
@@ -794,9 +801,9 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         return warp_max(gm);
     }
     // forward: record 0 is still in slot 0
-    double x = act ? s.x0[lane] : 0.0;
-    if (WRITE_X && act) Xo[lane] = x;
-    double r_n = (WRITE_X && act) ? qp.r[lane] : 0.0;   // target of the stage, register-prefetched one stage ahead
+    double x = (act && !refine) ? s.x0[lane] : 0.0;
+    if (WRITE_X && act && !refine) Xo[lane] = x;
+    double r_n = (WRITE_X && act && !refine) ? qp.r[lane] : 0.0;   // target of the stage, register-prefetched
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         const double *slot = rec_slot<CF>(s, t);
@@ -804,7 +811,9 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) {
             vec[lane] = x;
-            if (WRITE_X) {
+            if (refine) {
+                ws_rec<CF>(sr, t)[R_::XC + lane] += x;
+            } else if (WRITE_X) {
                 ws_rec<CF>(sr, t)[R_::XC + lane] = x - r_n;
                 r_n = qp.r[(t + 1) * N + lane];
             }
@@ -814,7 +823,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, lane);
         int mk[M];
         double hv[M], bq[M];
-        const double dq = act ? slot[R_::D + lane] : 0.0;
+        const double dq = (act && !refine) ? slot[R_::D + lane] : 0.0;
 #pragma unroll
         for (int a = 0; a < M; ++a) {
             mk[a] = s.mask[t * M + a];
@@ -838,17 +847,18 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             double uv = u[0];
 #pragma unroll
             for (int a = 1; a < M; ++a) uv = (lane == a) ? u[a] : uv;
-            s.Uo[t * M + lane] = uv;
+            s.Uo[t * M + lane] = refine ? s.Uo[t * M + lane] + uv : uv;
         }
         if (act) {
             double xn = ax + dq;
 #pragma unroll
             for (int a = 0; a < M; ++a) xn = fma(bq[a], u[a], xn);
             x = xn;
-            if (WRITE_X) Xo[(t + 1) * N + lane] = x;
+            if (refine) Xo[(t + 1) * N + lane] += x;
+            else if (WRITE_X) Xo[(t + 1) * N + lane] = x;
         }
     }
-    if (act) s.xT[lane] = x - (WRITE_X ? r_n : qp.r[H * N + lane]);
+    if (act) s.xT[lane] = refine ? s.xT[lane] + x : x - (WRITE_X ? r_n : qp.r[H * N + lane]);
     __syncwarp();
     // a non-finite state anywhere in the rollout propagates to x_H
     return __any_sync(FULL, !isfinite(x)) ? 1.0 : 0.0;
@@ -1032,40 +1042,57 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
             cnt.factor++;
             cnt.polish++;
             x_nonfinite = riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_POLISH, true, lane) != 0.0;
-            const double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
-                                           : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
-            const double gs = fmax(1.0, gmax);
-            bool changed = false, unstationary = false;
+            double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
+                                    : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
+            bool stable = false;
 #pragma unroll 1
-            for (int e = lane; e < HM; e += 32) {
-                const int t = e / M, i = e % M;
-                const int mk = s.mask[e];
-                const double u = s.Uo[e], g = s.kk[e];
-                const double lo = box_lo(s, qp.sat, t, i), hi = box_hi(s, qp.sat, t, i);
-                int nm = mk;
-                if (mk == 0) {
-                    if (u < lo - 1e-12) nm = 1;
-                    else if (u > hi + 1e-12) nm = 2;
-                    // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
-                    // cost-to-go has outgrown fp64 (long horizons with the order-1 model)
-                    unstationary |= !(fabs(g) <= 1e-6 * gs);
-                } else if (mk == 1) {
-                    if (g < -1e-10 * gs) nm = 0;
-                } else {
-                    if (g > 1e-10 * gs) nm = 0;
+            for (int rf = 0;; ++rf) {
+                const double gs = fmax(1.0, gmax);
+                bool changed = false, visible = false, unstationary = false;
+#pragma unroll 1
+                for (int e = lane; e < HM; e += 32) {
+                    const int t = e / M, i = e % M;
+                    const int mk = s.mask[e];
+                    const double u = s.Uo[e], g = s.kk[e];
+                    const double lo = box_lo(s, qp.sat, t, i), hi = box_hi(s, qp.sat, t, i);
+                    int nm = mk;
+                    if (mk == 0) {
+                        if (u < lo - 1e-12) nm = 1;
+                        else if (u > hi + 1e-12) nm = 2;
+                        // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
+                        // cost-to-go has outgrown fp64 (long horizons with the order-1 model)
+                        visible |= !(fabs(g) <= 1e-7 * gs);
+                        unstationary |= !(fabs(g) <= 1e-6 * gs);
+                    } else if (mk == 1) {
+                        if (g < -1e-10 * gs) nm = 0;
+                    } else {
+                        if (g > 1e-10 * gs) nm = 0;
+                    }
+                    if (nm != mk) {
+                        s.mask[e] = nm;
+                        changed = true;
+                    }
                 }
-                if (nm != mk) {
-                    s.mask[e] = nm;
-                    changed = true;
+                __syncwarp();
+                if (__any_sync(FULL, changed)) break;   // the working set moved: next round
+                // same working set again: certified if the free controls are stationary; a visible gradient means
+                // the Riccati solve lost accuracy (ill-conditioned cost-to-go) -- iterative refinement with the same
+                // factorisation, at most three times, then the ADMM fallback (and, in the end, exit code 2)
+                if (!__any_sync(FULL, visible) || (rf == 3 && !__any_sync(FULL, unstationary))) {
+                    stable = true;
+                    certified = !__any_sync(FULL, unstationary);
+                    break;
                 }
+                if (rf == 3) {
+                    stable = true;
+                    break;
+                }
+                x_nonfinite = riccati_solve<CF, FUSED, true>(sr, qp_in, 0.0, SWEEP_REFINE, true, lane) != 0.0;
+                cnt.admm += 2;   // one correction sweep + one adjoint sweep
+                gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
+                                 : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             }
-            __syncwarp();
-            if (!__any_sync(FULL, changed)) {
-                // same working set again: either it is certified, or the solve itself is not accurate enough and more
-                // rounds would repeat it -- hand over to the ADMM fallback (and, in the end, exit code 2)
-                certified = !__any_sync(FULL, unstationary);
-                break;
-            }
+            if (stable) break;
         }
         if (certified) {
             // warm start of the next solve: z = u*, y = the (scaled) multipliers of the pinned controls
