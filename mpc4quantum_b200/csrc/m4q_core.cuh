@@ -945,7 +945,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
 //   * primal-dual active set ("polish"): controls in the working set are pinned to their bound and folded into
 //     the dynamics, one masked Riccati factor + solve gives the equality-constrained optimum, and an adjoint
 //     gradient certifies the KKT conditions (multiplier signs on pinned controls, feasibility of free ones) or
-//     updates the set.  The certificate is a full KKT check: stationarity of the free controls (1e-6 relative),
+//     updates the set.  The certificate is a full KKT check: stationarity of the free controls (1e-8 relative),
 //     primal feasibility (1e-12), multiplier signs (1e-10 relative).
 // Tight mode (polish = 1): the working set is warm-started from the previous solve's (z, y) -- the previous SQP
 // iterate or the shifted previous MPC step -- and the active-set rounds run first; an ADMM block (which needs no
@@ -1061,8 +1061,8 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                         else if (u > hi + 1e-12) nm = 2;
                         // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
                         // cost-to-go has outgrown fp64 (long horizons with the order-1 model)
-                        visible |= !(fabs(g) <= 1e-7 * gs);
-                        unstationary |= !(fabs(g) <= 1e-6 * gs);
+                        visible |= !(fabs(g) <= 1e-9 * gs);
+                        unstationary |= !(fabs(g) <= 1e-8 * gs);
                     } else if (mk == 1) {
                         if (g < -1e-10 * gs) nm = 0;
                     } else {
