@@ -86,7 +86,7 @@ template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
 }
 
 template <class CF> struct Slab {
-    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr;
+    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr, *mbar;
     int *mask;
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
@@ -125,6 +125,7 @@ template <class CF> struct Slab {
         take(&q->va, N);
         take(&q->vb, N);
         take(&q->xT, N);
+        take(&q->mbar, 4);   // two mbarriers (one per record-ring slot) + their phase bits
         take(&q->lo0, M);
         take(&q->hi0, M);
         take(&q->xcur, 2 * dd);
@@ -180,6 +181,51 @@ template <int COUNT> __device__ __forceinline__ void prefetch_block(double *dst,
     for (int c = 0; c < cdiv(COUNT / 2, 32); ++c, sa += 512, ga += 512)
         if (c * 32 + lane < COUNT / 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(ga) : "memory");
     cp_async_commit();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Record ring of the vector sweeps, optional TMA variant (compile with -DM4Q_TMA_RING=1): whole stage records
+// (2.3 KB for the transmon) moved as 1-D bulk copies (cp.async.bulk, UBLKCP in SASS), one instruction of one lane per
+// record, completion on an mbarrier per ring slot.  The records are written through the generic proxy (plain stores of
+// this warp) and read by the bulk copy through the async proxy, so a proxy fence precedes every issue.  Measured on
+// B200 (transmon_h16, 65,536 members): LDGSTS ring 116.2 k trajectories/s; bulk copies with fence.proxy.async.global
+// 115.0 k, with the full fence.proxy.async 101.4 k -- no gain at this transfer size, so LDGSTS stays the default.
+// ---------------------------------------------------------------------------------------------------------
+#ifndef M4Q_TMA_RING
+#define M4Q_TMA_RING 0
+#endif
+#ifndef M4Q_PROXY_FENCE
+#define M4Q_PROXY_FENCE "fence.proxy.async.global;"
+#endif
+__device__ __forceinline__ void mbar_init(double *mbar, int lane) {
+    if (lane == 0) {
+        const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a + 8) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        reinterpret_cast<unsigned *>(mbar + 2)[0] = 0u;   // phase bits of the two slots
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void bulk_load(double *dst, const double *src, unsigned bytes, double *mbar_slot) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), m = (unsigned)__cvta_generic_to_shared(mbar_slot);
+    asm volatile(M4Q_PROXY_FENCE ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(m)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(double *mbar_slot, unsigned parity) {
+    const unsigned m = (unsigned)__cvta_generic_to_shared(mbar_slot);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(m),
+        "r"(parity)
+        : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -667,7 +713,26 @@ template <class CF> __device__ __forceinline__ double *rec_slot(const Slab<CF> &
 }
 template <class CF>
 __device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int lane) {
+#if M4Q_TMA_RING
+    if (lane == 0) bulk_load(rec_slot<CF>(s, t), ws_rec<CF>(sr, t), Rec<CF>::SIZE * 8, s.mbar + (t & 1));
+#else
     prefetch_block<Rec<CF>::SIZE>(rec_slot<CF>(s, t), ws_rec<CF>(sr, t), lane);
+#endif
+}
+// wait for record t; ph carries the phase bits of the two slots (uniform over the warp, kept in the slab between calls)
+template <class CF> __device__ __forceinline__ void ring_wait(const Slab<CF> &s, int t, unsigned &ph) {
+#if M4Q_TMA_RING
+    mbar_wait(s.mbar + (t & 1), (ph >> (t & 1)) & 1u);
+    ph ^= 1u << (t & 1);
+#else
+    cp_async_wait_all();
+#endif
+}
+template <class CF> __device__ __forceinline__ unsigned ring_phase_load(const Slab<CF> &s) {
+    return reinterpret_cast<const unsigned *>(s.mbar + 2)[0];
+}
+template <class CF> __device__ __forceinline__ void ring_phase_store(const Slab<CF> &s, unsigned ph, int lane) {
+    if (lane == 0) reinterpret_cast<unsigned *>(s.mbar + 2)[0] = ph;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -699,6 +764,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     // the refinement variant is a separate (cold) instantiation: the hot copy stays small for the instruction cache
     const bool adj = !REFINE && mode == SWEEP_ADJOINT, refine = REFINE;
     double *Xo = ws_Xo<CF>(sr);
+    unsigned ph = ring_phase_load<CF>(s);
     prefetch_stage<CF>(s, sr, H - 1, lane);
 #pragma unroll 1
     for (int e = lane; e < H * M; e += 32) {
@@ -754,7 +820,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
             dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
             ql_n = qp.qlin[(t - 1) * N + lane];
         }
-        cp_async_wait_all();
+        ring_wait<CF>(s, t, ph);
         __syncwarp();
         if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
         if (adj && act) ql = -2.0 * qp.Q[t * qp.q_stride + lane * N + lane] * slot[R_::XC + lane];
@@ -795,6 +861,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     }
     __syncwarp();   // kk complete; va/vb free again
     if (adj) {      // max |grad| over the horizon
+        ring_phase_store<CF>(s, ph, lane);
         double gm = 0.0;
 #pragma unroll 1
         for (int e = lane; e < H * M; e += 32) gm = fmax(gm, fabs(s.kk[e]));
@@ -818,7 +885,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
                 r_n = qp.r[(t + 1) * N + lane];
             }
         }
-        cp_async_wait_all();
+        if (t > 0) ring_wait<CF>(s, t, ph);   // record 0 is still in its slot from the backward sweep
         __syncwarp();
         if (t + 1 < H) prefetch_stage<CF>(s, sr, t + 1, lane);
         int mk[M];
@@ -859,6 +926,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         }
     }
     if (act) s.xT[lane] = refine ? s.xT[lane] + x : x - (WRITE_X ? r_n : qp.r[H * N + lane]);
+    ring_phase_store<CF>(s, ph, lane);
     __syncwarp();
     // a non-finite state anywhere in the rollout propagates to x_H
     return __any_sync(FULL, !isfinite(x)) ? 1.0 : 0.0;
@@ -894,6 +962,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
     const int H = sr.H;
     const bool act = lane < N;
     const double *Xo = ws_Xo<CF>(sr);
+    unsigned ph = ring_phase_load<CF>(s);
     prefetch_stage<CF>(s, sr, H - 1, lane);
     double xd_n = act ? Xo[(H - 1) * N + lane] - qp.r[(H - 1) * N + lane] : 0.0;
     if (act) s.P[lane] = Xo[H * N + lane] - qp.r[H * N + lane];   // P is dead outside the factor
@@ -914,7 +983,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
             xdv[lane] = xd;
             if (t > 0) xd_n = Xo[(t - 1) * N + lane] - qp.r[(t - 1) * N + lane];
         }
-        cp_async_wait_all();
+        ring_wait<CF>(s, t, ph);
         __syncwarp();
         if (t > 0) prefetch_stage<CF>(s, sr, t - 1, lane);
         double g[M];
@@ -934,6 +1003,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
         const double atl = cmatvec<CF, true>(At, lamv, lane);
         lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, xdv, lane);
     }
+    ring_phase_store<CF>(s, ph, lane);
     __syncwarp();
     return gmax;
 }

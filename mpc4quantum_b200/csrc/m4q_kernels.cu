@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     const Slab<CF> s = slab_view<CF>(sr);
     double *Xg = ws_Xg<CF>(sr);
     const double *Xo = ws_Xo<CF>(sr);
+    mbar_init(s.mbar, lane);
     double2 *xcur = reinterpret_cast<double2 *>(s.xcur);
     double2 *xmeas = reinterpret_cast<double2 *>(s.xmeas);
     double2 *scr2 = reinterpret_cast<double2 *>(s.scr);
@@ -544,6 +545,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
     const int H = a.H;
     SlabRef sr = {warp * a.slab_doubles, H, 1, C, nullptr};
     const Slab<CF> s = slab_view<CF>(sr);
+    mbar_init(s.mbar, lane);
 
     for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
         double *ws = a.ws + k * qp_ws_doubles<CF>(H);
