@@ -1243,6 +1243,12 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
     const int r = im ? lane - C : lane;
     const double sgn = im ? 1.0 : -1.0;
     double x_n = act ? Xg[lane] : 0.0;
+    // order-1 library (phi_k = u_k): the derivative weights are the identity and need not be tabulated per stage
+    bool first_order = p == M;
+    if (first_order) {
+#pragma unroll 1
+        for (int e = 0; e < M * M; ++e) first_order &= pow[e] == ((e / M == e % M) ? 1 : 0);
+    }
 #pragma unroll 1
     for (int t = 0; t < H; ++t) {
         double *dco = s.scr + (t & 1) * (p * M);   // [p][M]
@@ -1252,7 +1258,9 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
             if (t + 1 < H) x_n = Xg[(t + 1) * N + lane];
         }
         // monomials and derivative weights: lane k < p computes its own
-        if (lane < p) {
+        if (first_order) {
+            if (lane < M) s.phi[t * model.nblk + 1 + lane] = s.Ug[t * M + lane];
+        } else if (lane < p) {
             double phi = 1.0;
             double dw[M];
 #pragma unroll
@@ -1305,7 +1313,7 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
                 }
                 const double y = fma(sgn, q0 + q1, p0 + p1);
 #pragma unroll
-                for (int i = 0; i < M; ++i) b[i] = fma(dco[(kb - 1) * M + i], y, b[i]);
+                for (int i = 0; i < M; ++i) b[i] = first_order ? (kb - 1 == i ? y : b[i]) : fma(dco[(kb - 1) * M + i], y, b[i]);
             }
             double *rec = ws_rec<CF>(sr, t);
             double d = 0.0;
