@@ -688,64 +688,174 @@ struct LinArgs {
     int slab_doubles;
 };
 
+// One warp per (instance, stage): the stages of the stand-alone call are independent, so nothing is kept per
+// instance -- the model blocks sit in shared memory once per CTA, x_t / u_t / the monomial weights in a few words per
+// warp, and the outputs are written straight to HBM with coalesced 16-byte stores.  The row products y_k = N_k x_t
+// are spread over the lanes as (k, row) pairs; B_t[:, i] = sum_k dphi_k/du_i y_k and Delta_t = -B_t u_t are then
+// assembled per output element.
 template <class CF>
-__global__ void __launch_bounds__(CF::MAXW * 32) linearize_kernel(const LinArgs a) {
-    constexpr int C = CF::C, N = CF::N, M = CF::M;
+__host__ __device__ inline int lin_warp_doubles(int nblk) {
+    const int p = nblk - 1;
+    return rup(2 * CF::C + CF::M + nblk + p * CF::M + p + 2 * p * CF::C, 2);
+}
+
+template <class CF>
+__global__ void __launch_bounds__(256) linearize_stage_kernel(const LinArgs a) {
+    constexpr int C = CF::C, M = CF::M, CC = C * C;
     extern __shared__ double2 smem2[];
-    double *smem = reinterpret_cast<double *>(smem2);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wpc = blockDim.x >> 5;
-    const int H = a.H;
-    const int slab_only = rup(Slab<CF>::doubles(H, a.nblk, C), 2);
-    const SlabRef sr = {warp * a.slab_doubles, H, a.nblk, C, smem + (size_t)warp * a.slab_doubles + slab_only};
-    const Slab<CF> s = slab_view<CF>(sr);
-    double *wXg = ws_Xg<CF>(sr);
-    StageOps model;
-    model.blocks = a.A_blocks;
-    model.nblk = a.nblk;
-    model.stage_stride = 0;
-    model.soff = 0;
-    for (long long k = (long long)blockIdx.x * wpc + warp; k < a.n_inst; k += (long long)gridDim.x * wpc) {
-        const double2 *Xk = a.Xg + (size_t)k * C * (H + 1);
-        const double *Uk = a.Ug + (size_t)k * M * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int H = a.H, nblk = a.nblk, p = nblk - 1;
+    double2 *blk = smem2;   // [nblk][C][C]
+    double *wbase = reinterpret_cast<double *>(smem2 + (size_t)nblk * CC) + (size_t)warp * lin_warp_doubles<CF>(nblk);
+    double2 *xs = reinterpret_cast<double2 *>(wbase);    // x_t [C]
+    double2 *ys = xs + C;                                // y_k [p][C]
+    double *ut = reinterpret_cast<double *>(ys + p * C); // u_t [M]
+    double *phi = ut + M, *dw = phi + nblk, *gk = dw + p * M;   // phi [nblk], dphi [p][M], g_k = sum_i u_i dphi_k/du_i
 #pragma unroll 1
-        for (int e = lane; e < (H + 1) * N; e += 32) {
-            const int t = e / N, kk = e % N;
-            const double2 v = Xk[(kk % C) * (H + 1) + t];
-            wXg[e] = kk < C ? v.x : v.y;
-        }
+    for (int e = threadIdx.x; e < nblk * CC; e += blockDim.x) blk[e] = a.A_blocks[e];
+    bool first_order = p == M;
+    if (first_order) {
 #pragma unroll 1
-        for (int e = lane; e < H * M; e += 32) s.Ug[e] = Uk[(e % M) * H + e / M];
-        __syncwarp();
-        linearize<CF, false>(sr, model, a.powers, lane);
-        double2 *Ao = a.A_out + (size_t)k * H * C * C;
-        double2 *Bo = a.B_out + (size_t)k * H * C * M;
-        double2 *Do = a.D_out + (size_t)k * H * C;
+        for (int e = 0; e < M * M; ++e) first_order &= a.powers[e] == ((e / M == e % M) ? 1 : 0);
+    }
+    __syncthreads();
+    const long long total = a.n_inst * H;
+    const long long stride = (long long)gridDim.x * wpc;
+    long long item = (long long)blockIdx.x * wpc + warp;
+    long long k = item / H;
+    int t = (int)(item - k * H);
+    const long long sk = stride / H;
+    const int st = (int)(stride - sk * H);
+    // x_t and u_t of the NEXT item are fetched into registers while the current one is processed
+    double2 x_n = make_double2(0.0, 0.0);
+    double u_n = 0.0;
+    if (item < total) {
+        if (lane < C) x_n = a.Xg[(size_t)k * C * (H + 1) + lane * (H + 1) + t];
+        if (lane < M) u_n = a.Ug[(size_t)k * M * H + lane * H + t];
+    }
 #pragma unroll 1
-        for (int e = lane; e < H * C * C; e += 32) {
-            const int t = e / (C * C), ij = e % (C * C);
-            double2 acc = make_double2(0.0, 0.0);
-            for (int kb = 0; kb < a.nblk; ++kb) {
-                const double2 v = a.A_blocks[kb * C * C + ij];
-                const double ph = s.phi[t * a.nblk + kb];
-                acc.x = fma(ph, v.x, acc.x);
-                acc.y = fma(ph, v.y, acc.y);
+    for (; item < total; item += stride) {
+        if (lane < C) xs[lane] = x_n;
+        if (lane < M) ut[lane] = u_n;
+        {
+            int t2 = t + st;
+            long long k2 = k + sk;
+            if (t2 >= H) {
+                t2 -= H;
+                ++k2;
             }
-            Ao[e] = acc;
-        }
-#pragma unroll 1
-        for (int e = lane; e < H * C * M; e += 32) {
-            const int t = e / (C * M), rem = e % (C * M), r = rem / M, i = rem % M;
-            const double *rec = ws_rec<CF>(sr, t);
-            Bo[e] = make_double2(rec[Rec<CF>::B + Rec<CF>::pair(i, r)], rec[Rec<CF>::B + Rec<CF>::pair(i, C + r)]);
-        }
-#pragma unroll 1
-        for (int e = lane; e < H * C; e += 32) {
-            const int t = e / C, r = e % C;
-            const double *rec = ws_rec<CF>(sr, t);
-            Do[e] = make_double2(rec[Rec<CF>::D + r], rec[Rec<CF>::D + C + r]);
+            if (item + stride < total) {
+                if (lane < C) x_n = a.Xg[(size_t)k2 * C * (H + 1) + lane * (H + 1) + t2];
+                if (lane < M) u_n = a.Ug[(size_t)k2 * M * H + lane * H + t2];
+            }
         }
         __syncwarp();
+        // monomials phi_k(u_t), their derivative weights (linearize.py:37-58) and g_k
+        if (first_order) {
+            if (lane < M) phi[1 + lane] = ut[lane];
+        } else {
+#pragma unroll 1
+            for (int kb = lane; kb < p; kb += 32) {
+                double ph = 1.0, dwl[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) dwl[i] = (double)a.powers[kb * M + i];
+#pragma unroll
+                for (int l = 0; l < M; ++l) {
+                    const int e = a.powers[kb * M + l];
+                    const double ul = ut[l];
+                    double pw = 1.0, pwm1 = 1.0;
+#pragma unroll 1
+                    for (int q = 0; q < e; ++q) {
+                        pwm1 = pw;
+                        pw *= ul;
+                    }
+                    ph *= pw;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) dwl[i] *= (i == l) ? (e > 0 ? pwm1 : 0.0) : pw;
+                }
+                double g = 0.0;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    dw[kb * M + i] = dwl[i];
+                    g = fma(dwl[i], ut[i], g);
+                }
+                phi[1 + kb] = ph;
+                gk[kb] = g;
+            }
+        }
+        if (lane == 0) phi[0] = 1.0;
+        // y_k[r] = (N_k x_t)[r], one (k, r) pair per lane
+        double2 x[C];
+#pragma unroll
+        for (int j = 0; j < C; ++j) x[j] = xs[j];
+#pragma unroll 1
+        for (int e = lane; e < p * C; e += 32) {
+            const double2 *row = blk + CC + e * C;   // block 1 + e / C, row e % C
+            double2 y0 = make_double2(0.0, 0.0), y1 = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                if (j & 1) y1 = cfma(row[j], x[j], y1);
+                else y0 = cfma(row[j], x[j], y0);
+            }
+            ys[e] = make_double2(y0.x + y1.x, y0.y + y1.y);
+        }
+        __syncwarp();
+        double2 *Ao = a.A_out + (size_t)item * CC;
+#pragma unroll
+        for (int q = 0; q < (CC + 31) / 32; ++q) {
+            const int e = lane + 32 * q;
+            if (e < CC) {
+                double2 acc = blk[e];
+#pragma unroll 2
+                for (int kb = 1; kb < nblk; ++kb) {
+                    const double2 v = blk[kb * CC + e];
+                    const double w = phi[kb];
+                    acc.x = fma(w, v.x, acc.x);
+                    acc.y = fma(w, v.y, acc.y);
+                }
+                Ao[e] = acc;
+            }
+        }
+        double2 *Bo = a.B_out + (size_t)item * C * M;
+#pragma unroll
+        for (int q = 0; q < (C * M + 31) / 32; ++q) {
+            const int e = lane + 32 * q;
+            if (e < C * M) {
+                const int r = e / M, i = e % M;
+                double2 b;
+                if (first_order) {
+                    b = ys[i * C + r];
+                } else {
+                    b = make_double2(0.0, 0.0);
+#pragma unroll 1
+                    for (int kb = 0; kb < p; ++kb) {
+                        const double w = dw[kb * M + i];
+                        const double2 y = ys[kb * C + r];
+                        b.x = fma(w, y.x, b.x);
+                        b.y = fma(w, y.y, b.y);
+                    }
+                }
+                Bo[e] = b;
+            }
+        }
+        if (lane < C) {
+            double2 d = make_double2(0.0, 0.0);
+#pragma unroll 1
+            for (int kb = 0; kb < p; ++kb) {
+                const double g = first_order ? ut[kb] : gk[kb];
+                const double2 y = ys[kb * C + lane];
+                d.x = fma(-g, y.x, d.x);
+                d.y = fma(-g, y.y, d.y);
+            }
+            a.D_out[(size_t)item * C + lane] = d;
+        }
+        __syncwarp();
+        t += st;
+        k += sk;
+        if (t >= H) {
+            t -= H;
+            ++k;
+        }
     }
 }
 
@@ -869,6 +979,123 @@ __global__ void __launch_bounds__(256) expm_step_kernel(long long n, int d, int 
             conjugate(rho, T0, d, G, lane);
             if (lane < dd) rho_out[((size_t)k * n_seg + sgm) * dd + lane] = rho[lane];
             __syncwarp();
+        }
+    }
+}
+
+// Same computation with ONE THREAD per member and the matrices in registers (d <= 4): no shared memory, no warp
+// syncs, every lane busy.  The warp-per-member version above keeps 32 - d*d lanes idle and is latency bound
+// (5 % of HBM on 3x3 matrices); this one streams parameters and states near the HBM / fp64 limits.
+template <int D>
+__global__ void __launch_bounds__(128) expm_step_kernel_t(long long n, int m, int n_seg, double dt, const double2 *H0,
+                                                          const double2 *H1, int shared_ham, const double *u,
+                                                          const double2 *rho_in, double2 *rho_out, double2 *prop_out) {
+    constexpr int DD = D * D;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const double2 *H0k = H0 + (shared_ham ? 0 : (size_t)k * DD);
+        const double2 *H1k = H1 + (shared_ham ? 0 : (size_t)k * m * DD);
+        double2 rho[DD];
+#pragma unroll
+        for (int e = 0; e < DD; ++e) rho[e] = rho_in[(size_t)k * DD + e];
+        for (int sgm = 0; sgm < n_seg; ++sgm) {
+            double2 G[DD], T[DD];
+#pragma unroll
+            for (int e = 0; e < DD; ++e) G[e] = H0k[e];
+            for (int i = 0; i < m; ++i) {
+                const double uu = u[((size_t)k * n_seg + sgm) * m + i];
+#pragma unroll
+                for (int e = 0; e < DD; ++e) {
+                    const double2 h1 = H1k[i * DD + e];
+                    G[e].x = fma(uu, h1.x, G[e].x);
+                    G[e].y = fma(uu, h1.y, G[e].y);
+                }
+            }
+            // G = -i H dt, 1-norm, scaling by a power of two to ||G||_1 <= 1/2 (same schedule as expm_minus_i)
+            double nrm = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                double cs = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double2 h = G[i * D + j];
+                    G[i * D + j] = make_double2(h.y * dt, -h.x * dt);
+                    cs += hypot(h.y * dt, h.x * dt);
+                }
+                nrm = fmax(nrm, cs);
+            }
+            int sq = 0;
+            while (nrm > 0.5 && sq < 40) {
+                nrm *= 0.5;
+                ++sq;
+            }
+            const double sc = ldexp(1.0, -sq);
+#pragma unroll
+            for (int e = 0; e < DD; ++e) {
+                G[e].x *= sc;
+                G[e].y *= sc;
+                T[e] = make_double2((e / D == e % D) ? 1.0 : 0.0, 0.0);
+            }
+            // Horner: T = I + G/1 (I + G/2 (I + ... (I + G/16)))
+#pragma unroll 1
+            for (int kk = 16; kk >= 1; --kk) {
+                const double inv = 1.0 / (double)kk;
+                double2 V[DD];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int q = 0; q < D; ++q) acc = cfma(G[i * D + q], T[q * D + j], acc);
+                        V[i * D + j] = make_double2(fma(acc.x, inv, i == j ? 1.0 : 0.0), acc.y * inv);
+                    }
+#pragma unroll
+                for (int e = 0; e < DD; ++e) T[e] = V[e];
+            }
+#pragma unroll 1
+            for (int q2 = 0; q2 < sq; ++q2) {
+                double2 V[DD];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int q = 0; q < D; ++q) acc = cfma(T[i * D + q], T[q * D + j], acc);
+                        V[i * D + j] = acc;
+                    }
+#pragma unroll
+                for (int e = 0; e < DD; ++e) T[e] = V[e];
+            }
+            if (prop_out) {
+#pragma unroll
+                for (int e = 0; e < DD; ++e) prop_out[((size_t)k * n_seg + sgm) * DD + e] = T[e];
+            }
+            // rho <- T rho T^dagger
+            double2 V[DD];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) acc = cfma(T[i * D + q], rho[q * D + j], acc);
+                    V[i * D + j] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) {
+                        const double2 tc = T[j * D + q];
+                        acc = cfma(V[i * D + q], make_double2(tc.x, -tc.y), acc);
+                    }
+                    rho[i * D + j] = acc;
+                }
+#pragma unroll
+            for (int e = 0; e < DD; ++e) rho_out[((size_t)k * n_seg + sgm) * DD + e] = rho[e];
         }
     }
 }
@@ -1172,6 +1399,21 @@ int m4q_expm_step_batched(int64_t N, int32_t d, int32_t m, int32_t n_seg, double
     if (N <= 0) return 0;
     if (d < 1 || d * d > 32) return fail("plant dimension out of range (d*d <= 32)");
     if (!H0 || !H1 || !u || !rho_in || !rho_out) return fail("null pointer");
+    if (d <= 4 && N >= 4096) {   // thread-per-member kernel once there are enough members to fill the GPU
+        long long tctas = (N + 127) / 128;
+        if (tctas > 148 * 16) tctas = 148 * 16;
+#define M4Q_EXPM_T(D_)                                                                                                  \
+    expm_step_kernel_t<D_><<<(int)tctas, 128, 0, (cudaStream_t)stream>>>(                                               \
+        N, m, n_seg, dt, (const double2 *)H0, (const double2 *)H1, shared_hamiltonian, u, (const double2 *)rho_in,      \
+        (double2 *)rho_out, (double2 *)prop_out)
+        if (d == 1) M4Q_EXPM_T(1);
+        else if (d == 2) M4Q_EXPM_T(2);
+        else if (d == 3) M4Q_EXPM_T(3);
+        else M4Q_EXPM_T(4);
+#undef M4Q_EXPM_T
+        M4Q_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int wpc = 8;
     long long ctas = (N + wpc - 1) / wpc;
     if (ctas > 148 * 8) ctas = 148 * 8;
@@ -1213,13 +1455,18 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
     a.A_out = (double2 *)A_out;
     a.B_out = (double2 *)B_out;
     a.D_out = (double2 *)D_out;
+    if (H < 1) return fail("linearize: horizon out of range");
     M4Q_DISPATCH(c, m, {
-        Geometry g;
-        if (!Slab<CF>::scratch_fits(p + 1, CF::C)) return fail("model too large for the slab scratch");
-        const int slab = rup(Slab<CF>::doubles(H, p + 1, CF::C), 2) + rup(ws_doubles<CF>(H), 2);
-        if (plan(linearize_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
-        a.slab_doubles = slab;
-        linearize_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
+        const int wpc = 8;
+        const size_t smem = (size_t)(p + 1) * c * c * sizeof(double2) + (size_t)wpc * lin_warp_doubles<CF>(p + 1) * sizeof(double);
+        if (smem > 200 * 1024) return fail("model too large for the shared-memory linearisation kernel");
+        M4Q_CUDA(cudaFuncSetAttribute(linearize_stage_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        M4Q_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, linearize_stage_kernel<CF>, wpc * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long ctas = (N * H + wpc - 1) / wpc;
+        if (ctas > 148LL * per_sm) ctas = 148LL * per_sm;
+        linearize_stage_kernel<CF><<<(int)ctas, wpc * 32, smem, (cudaStream_t)stream>>>(a);
     });
     M4Q_CUDA(cudaGetLastError());
     return 0;

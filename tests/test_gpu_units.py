@@ -80,6 +80,39 @@ def test_expm_propagators(unit_golden, tag, maker):
     assert np.abs(np.einsum('nii->n', states[:, -1].reshape(16, d, d)) - 1).max() < 1e-12
 
 
+@pytest.mark.parametrize('maker', [systems.ensemble_qubit, systems.ensemble_transmon, systems.ensemble_crosstalk])
+@pytest.mark.parametrize('shared', [False, True])
+def test_expm_large_ensembles_use_the_thread_per_member_kernel(maker, shared):
+    """N >= 4096 and d <= 4 dispatch to the register-resident thread-per-member kernel; it must agree with
+    scipy.linalg.expm (north_star 1e-10) and with the warp-per-member kernel (N < 4096) on the same members."""
+    from scipy.linalg import expm
+    n, n_seg, dt = 8192, 4, 0.25
+    ens, _ = maker(n)
+    d, m = ens.d, ens.H1.shape[1]
+    rng = np.random.default_rng(11)
+    u = rng.uniform(-1.5, 1.5, size=(n, n_seg, m))
+    psi = rng.normal(size=(n, d)) + 1j * rng.normal(size=(n, d))
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    rho0 = np.einsum('ni,nj->nij', psi, psi.conj()).reshape(n, d * d)
+    H0, H1 = (ens.H0[5], ens.H1[5]) if shared else (ens.H0, ens.H1)
+    big, bigp = expm_segments(rho0, H0, H1, u, dt, shared=shared, return_propagators=True)
+    sub = slice(1000, 1064)
+    small, smallp = expm_segments(rho0[sub], H0 if shared else H0[sub], H1 if shared else H1[sub], u[sub], dt,
+                                  shared=shared, return_propagators=True)
+    big, bigp, small, smallp = (t.cpu().numpy() for t in (big, bigp, small, smallp))
+    assert np.abs(bigp[sub] - smallp).max() < 1e-13
+    assert np.abs(big[sub] - small).max() < 1e-13
+    for k in (0, 17, 4095, 4096, n - 1):
+        h0, h1 = (H0, H1) if shared else (H0[k], H1[k])
+        rho = rho0[k].reshape(d, d)
+        for sgm in range(n_seg):
+            P = expm(-1j * dt * (h0 + np.einsum('i,ijk->jk', u[k, sgm], h1)))
+            assert np.abs(bigp[k, sgm] - P).max() < 1e-13
+            rho = P @ rho @ P.conj().T
+            assert np.abs(big[k, sgm] - rho.reshape(-1)).max() < 1e-12
+    assert np.abs(np.einsum('nii->n', big[:, -1].reshape(n, d, d)) - 1).max() < 1e-12
+
+
 @pytest.mark.parametrize('tag', ['qubit', 'transmon', 'cross'])
 @pytest.mark.parametrize('polish', [1, 0])
 def test_quad_program(qp_golden, tag, polish):
