@@ -27,6 +27,10 @@ UNIT = 'trajectories/s'
 
 
 # ----------------------------------------------------------------------------------------------------------
+SYSTEM_NAMES = {'transmon': '3-level transmon', 'qubit': 'ideal qubit', 'crosstalk': 'two qubits with ZZ crosstalk',
+                'not_gate': 'NOT-gate synthesis on the qubit process vector'}
+
+
 def workload(name, discretize=None):
     from mpc4quantum_b200 import systems
     if name.startswith('transmon_h') or name.startswith('transmon_o2_h'):
@@ -37,6 +41,8 @@ def workload(name, discretize=None):
         return systems.config_qubit(1, discretize=discretize), systems.ensemble_qubit
     if name == 'crosstalk':
         return systems.config_crosstalk(0.0, discretize=discretize), systems.ensemble_crosstalk
+    if name == 'not_gate':      # gate synthesis on process vectors (c = 16, m = 1, H = 15, S = 50)
+        return systems.config_not_gate(1, discretize=discretize), systems.ensemble_not_gate
     raise SystemExit('unknown workload %s' % name)
 
 
@@ -105,7 +111,8 @@ def _cpu_member(job):
     ens, _ = maker(n_total)
     mem = ens.member(k)
     lift, proj = (rs.lift_coupled, rs.proj_coupled) if cfg.get('kind') == 'coupled' else (rs.lift_identity, rs.lift_identity)
-    plant = rs.ExpmPlant(mem.H0, mem.H1_list, lift, proj)
+    plant = rs.ProcessPlant(mem.H0, mem.H1_list) if cfg.get('kind') == 'process' else \
+        rs.ExpmPlant(mem.H0, mem.H1_list, lift, proj)
     stats = {}
     xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
                              cfg['clock'].horizon, cfg['clock'].n_steps, plant, cfg['model'].A, cfg['Q'], cfg['R'],
@@ -212,7 +219,8 @@ def main():
     # ---- resident inputs (value) and pinned host inputs (e2e)
     H0_h = torch.from_numpy(np.ascontiguousarray(ens.H0)).pin_memory()
     H1_h = torch.from_numpy(np.ascontiguousarray(ens.H1)).pin_memory()
-    x0_h = torch.from_numpy(np.ascontiguousarray(cfg['x0'].reshape(1, -1))).pin_memory()
+    x0_plant = cfg['u0'] if cfg.get('kind') == 'process' else cfg['x0']     # gate synthesis: the propagator itself
+    x0_h = torch.from_numpy(np.ascontiguousarray(x0_plant.reshape(1, -1))).pin_memory()
     H0_d, H1_d, x0_d = H0_h.cuda(), H1_h.cuda(), x0_h.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')      # > 126 MB L2
     hist = torch.zeros(256, dtype=torch.int64, device='cuda')
@@ -348,8 +356,9 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '%s: 3-level transmon (c=%d, m=%d), horizon %d, %d MPC steps, %d perturbed plants per GPU '
-                               '(seed 20220113), tight QP mode (%s)' % (args.workload, cfg['model'].A.shape[0], cfg['dim_u'],
+        'config': {'workload': '%s: %s (c=%d, m=%d), horizon %d, %d MPC steps, %d perturbed plants per GPU '
+                               '(seed 20220113), tight QP mode (%s)' % (args.workload, SYSTEM_NAMES.get(cfg['name'], cfg['name']),
+                                                                   cfg['model'].A.shape[0], cfg['dim_u'],
                                                                    cfg['clock'].horizon, S, args.members,
                                                                    'ADMM block first' if args.admm_first else
                                                                    'warm active set first, ADMM fallback'),

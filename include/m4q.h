@@ -31,6 +31,7 @@ extern "C" {
 #define M4Q_LIFT_IDENTITY 0
 #define M4Q_LIFT_COUPLED  1   /* QCoupledExperiment: stacked partial traces / Kronecker product */
 #define M4Q_LIFT_TRUNC32  2   /* QExperiment32: qubit block of a qutrit, trace-normalised        */
+#define M4Q_LIFT_PROCESS  3   /* QSynthesis: plant state = propagator U, model state = vec(U (x) U^*) */
 
 /* QP solver settings (replaces the cvxpy->OSQP call at optimize.py:59) */
 typedef struct {

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libm4q.so')
 
-LIFT_IDENTITY, LIFT_COUPLED, LIFT_TRUNC32 = 0, 1, 2
+LIFT_IDENTITY, LIFT_COUPLED, LIFT_TRUNC32, LIFT_PROCESS = 0, 1, 2, 3
 
 c_i32, c_i64, c_f64, c_vp = ct.c_int32, ct.c_int64, ct.c_double, ct.c_void_p
 

@@ -40,6 +40,7 @@ template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };   //
 template <> struct Tiles<9, 2> { static constexpr int MAXW = 12; };   // 3 warps per scheduler: 168 registers, no spills
 template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };   // 15 fit; measured faster than 12 x 168 registers
 template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
+template <> struct Tiles<16, 1> { static constexpr int MAXW = 8; };
 
 template <int C_, int M_> struct Cfg {
     static constexpr int C = C_, N = 2 * C_, M = M_, Q = N + M_;
@@ -1537,6 +1538,15 @@ __device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, do
     }
     __syncwarp();
     if (act) rho[lane] = v;
+    __syncwarp();
+}
+
+// U <- T U (gate synthesis: the plant state is the propagator itself, experiment.py:371-401)
+__device__ __noinline__ void left_multiply(double2 *U, const double2 *T, int d, double2 *tmp, int lane) {
+    const bool act = lane < d * d;
+    if (act) tmp[lane] = cmm(T, U, d, lane / d, lane % d);
+    __syncwarp();
+    if (act) U[lane] = tmp[lane];
     __syncwarp();
 }
 

@@ -148,6 +148,17 @@ __device__ void lift_state(int mode, int d, const double2 *rho, double *out, int
             out[lane] = acc.x;
             out[C + lane] = acc.y;
         }
+    } else if (mode == M4Q_LIFT_PROCESS) {
+        // plant state = propagator U [d][d]; model state = vec(U (x) U^*), C = d^4 (experiment.py:357-369):
+        // element (i d + k) d^2 + (j d + l) = U[i][j] conj(U[k][l])
+        const int d2 = d * d;
+        if (lane < C) {
+            const int row = lane / d2, col = lane % d2;
+            const double2 a = rho[(row / d) * d + col / d], b = rho[(row % d) * d + col % d];
+            const double2 v = cmul(a, make_double2(b.x, -b.y));
+            out[lane] = v.x;
+            out[C + lane] = v.y;
+        }
     } else {   // M4Q_LIFT_TRUNC32: qubit block of a qutrit divided by its trace norm (sum of singular values)
         const double2 a = rho[0], b = rho[1], c = rho[3], e = rho[4];
         const double fro = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + e.x * e.x + e.y * e.y;
@@ -181,6 +192,26 @@ __device__ void proj_state(int mode, int d, const double *x, double2 *rho, int l
         if (lane < C) rho[lane] = make_double2(x[lane], x[C + lane]);
     }
     __syncwarp();
+}
+
+// Re <w, observed state>: the plant state itself (<psi|rho|psi> for w = vec(|psi><psi|)), or, for gate synthesis,
+// the lifted process vector (|tr(Uf^+ U)|^2 / d^2 for w = vec(Uf (x) Uf^*) / d^2).
+template <class CF>
+__device__ double fidelity_of(int mode, int d, const double2 *w, const double2 *xcur, double *scratch, int lane) {
+    constexpr int C = CF::C;
+    double f = 0.0;
+    if (mode == M4Q_LIFT_PROCESS) {
+        lift_state<CF>(mode, d, xcur, scratch, lane);
+        if (lane < C) {
+            const double2 wv = w[lane];
+            f = wv.x * scratch[lane] + wv.y * scratch[C + lane];
+        }
+        __syncwarp();
+    } else if (lane < d * d) {
+        const double2 wv = w[lane], x = xcur[lane];
+        f = wv.x * x.x + wv.y * x.y;
+    }
+    return warp_sum(f);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -409,7 +440,8 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                             }
                             __syncwarp();
                             expm_minus_i(scr2, a.dt, d, scr2 + dd, scr2 + 2 * dd, scr2 + 3 * dd, lane);
-                            conjugate(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
+                            if (a.lift_mode == M4Q_LIFT_PROCESS) left_multiply(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
+                            else conjugate(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
                         }
                         if (lane < dd) xcur[lane] = xmeas[lane];
                         __syncwarp();
@@ -452,12 +484,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
 
                 // built-in exit condition: infidelity of the new plant state below a threshold (mpc.py:289-292)
                 if (!a.external_plant && a.exit_infid > 0.0 && a.fid_vec) {
-                    double f = 0.0;
-                    if (lane < dd) {
-                        const double2 w = a.fid_vec[lane], x = xcur[lane];
-                        f = w.x * x.x + w.y * x.y;
-                    }
-                    f = warp_sum(f);
+                    const double f = fidelity_of<CF>(a.lift_mode, d, a.fid_vec, xcur, s.va, lane);
                     if (1.0 - f < a.exit_infid) {
                         exit_code = 1;
                         ++step;
@@ -481,12 +508,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
             }
         }
         if (a.fidelity && !a.external_plant && a.fid_vec) {
-            double f = 0.0;
-            if (lane < dd) {
-                const double2 w = a.fid_vec[lane], x = xcur[lane];
-                f = w.x * x.x + w.y * x.y;
-            }
-            f = warp_sum(f);
+            const double f = fidelity_of<CF>(a.lift_mode, d, a.fid_vec, xcur, s.va, lane);
             if (lane == 0) a.fidelity[k] = f;
         }
         if (a.state) {
@@ -1353,11 +1375,13 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
         else if ((c) == 9 && (m) == 2) { using CF = Cfg<9, 2>; __VA_ARGS__; }         \
         else if ((c) == 8 && (m) == 2) { using CF = Cfg<8, 2>; __VA_ARGS__; }         \
         else if ((c) == 16 && (m) == 3) { using CF = Cfg<16, 3>; __VA_ARGS__; }       \
+        else if ((c) == 16 && (m) == 1) { using CF = Cfg<16, 1>; __VA_ARGS__; }       \
         else return fail("unsupported (c, m): no compiled instantiation");            \
     } while (0)
 
 static bool supported(int c, int m) {
-    return (c == 4 && m == 1) || (c == 4 && m == 2) || (c == 9 && m == 2) || (c == 8 && m == 2) || (c == 16 && m == 3);
+    return (c == 4 && m == 1) || (c == 4 && m == 2) || (c == 9 && m == 2) || (c == 8 && m == 2) || (c == 16 && m == 3) ||
+           (c == 16 && m == 1);
 }
 
 static int check_problem(const m4q_mpc_problem *p) {
@@ -1372,6 +1396,9 @@ static int check_problem(const m4q_mpc_problem *p) {
     if (p->lift_mode == M4Q_LIFT_COUPLED && !((p->d == 4 && p->c == 8) || (p->d == 9 && p->c == 18)))
         return fail("coupled lift needs d = dA^2 and c = 2 dA^2");
     if (p->lift_mode == M4Q_LIFT_TRUNC32 && !(p->d == 3 && p->c == 4)) return fail("trunc32 lift needs d = 3, c = 4");
+    if (p->lift_mode == M4Q_LIFT_PROCESS && !(p->d == 2 && p->c == 16)) return fail("process lift needs d = 2, c = d^4 = 16");
+    if (p->lift_mode == M4Q_LIFT_PROCESS && p->measure_freq != 1)
+        return fail("process lift: the propagator cannot be recovered from a model step, measure_freq must be 1");
     if (p->lift_mode == M4Q_LIFT_TRUNC32 && p->measure_freq != 1)
         return fail("QExperiment32.proj is not a map back to the plant space (experiment.py:232-235); measure_freq must be 1");
     if (!(p->sat > 0)) return fail("sat is mandatory (optimize.py:43)");
@@ -1479,6 +1506,7 @@ int64_t m4q_qp_workspace_bytes(int64_t N, int32_t c, int32_t m, int32_t H) {
     else if (c == 9 && m == 2) per = qp_ws_doubles<Cfg<9, 2>>(H);
     else if (c == 8 && m == 2) per = qp_ws_doubles<Cfg<8, 2>>(H);
     else if (c == 16 && m == 3) per = qp_ws_doubles<Cfg<16, 3>>(H);
+    else if (c == 16 && m == 1) per = qp_ws_doubles<Cfg<16, 1>>(H);
     if (per < 0) {
         fail("unsupported (c, m): no compiled instantiation");
         return -1;

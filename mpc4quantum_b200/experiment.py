@@ -162,12 +162,103 @@ class QCoupledExperiment(QExperiment):
         return np.kron(v[:half].reshape(dA, dA), v[half:].reshape(dA, dA)).flatten()
 
 
+class QSynthesis(Experiment):
+    """Gate synthesis (experiment.py:336-417): the plant state is a propagator U, observed through its process
+    matrix P = U (x) U^* (the "density matrix of a unitary").  ``simulate`` takes and returns process vectors.
+
+    The reference evaluates qutip.propagator under the piecewise-constant control; here every constant segment is
+    the exact factor expm(-i (H0 + sum_k u_k H1_k) dt) from ``m4q_expm_step_batched``.
+    """
+
+    def __init__(self, H0, H1_list):
+        super().__init__()
+        self.H0 = _as_matrix(H0)
+        self.H1_list = [_as_matrix(h) for h in H1_list]
+        self._prop_args = {}
+
+    def f(self, t, x, u):
+        return self.H0 * x + np.sum([H1 * x * u1 for H1, u1 in zip(self.H1_list, u)], axis=0)
+
+    def set(self, key, value):
+        self._prop_args[key] = value
+
+    @staticmethod
+    def lift(U):
+        """Flat propagator (n^2,) -> flat process matrix (n^4,), P = U (x) U^* (experiment.py:357-369)."""
+        n = isqrt(np.shape(U)[0])
+        U = np.asarray(U, dtype=complex).reshape(n, n)
+        return np.kron(U, U.conj()).flatten()
+
+    @staticmethod
+    def proj(P):
+        """Flat process matrix (n^4,) -> a flat propagator equal to U up to a global phase (experiment.py:371-388):
+        the first non-zero n x n block of P, block (i, j), is U[i, j] conj(U); its own (i, j) entry is |U[i, j]|^2,
+        so conj(block) / sqrt(that entry) = exp(-i arg U[i, j]) U."""
+        P = np.asarray(P, dtype=complex)
+        n = isqrt(isqrt(P.shape[0]))
+        blocks = split_blocks(P.reshape(n ** 2, n ** 2), n, n)
+        U = np.zeros((n, n))
+        for i, b in enumerate(blocks):
+            if np.any(b):
+                U = b.conj() / np.lib.scimath.sqrt(b.flatten()[i])
+                break
+        return U.flatten()
+
+    def propagators(self, ts, us):
+        """Segment factors V_i = expm(-i H(u_i) (ts[i+1] - ts[i])), shape [len(ts) - 1, n, n]."""
+        ts = np.asarray(ts, dtype=float)
+        u_seg = _controls_on_grid(us, ts)
+        steps = np.diff(ts)
+        n = self.H0.shape[0]
+        eye = np.eye(n, dtype=complex).reshape(1, -1)
+        H1 = np.stack(self.H1_list)
+        if len(steps) and np.allclose(steps, steps[0], rtol=1e-12, atol=0):
+            _, props = expm_segments(eye, self.H0, H1, u_seg[None], steps[0], shared=True, return_propagators=True)
+            return props[0].cpu().numpy()
+        out = [expm_segments(eye, self.H0, H1, u_seg[None, i:i + 1], h, shared=True,
+                             return_propagators=True)[1][0, 0].cpu().numpy() for i, h in enumerate(steps)]
+        return np.array(out).reshape(-1, n, n)
+
+    def simulate(self, x0, ts, us):
+        n = self.H0.shape[0]
+        self.ts, self.us = ts, us
+        U = QSynthesis.proj(np.asarray(x0, dtype=complex).reshape(-1)).reshape(n, n)
+        cols = [QSynthesis.lift(U.flatten())]
+        for V in self.propagators(ts, us):
+            U = V @ U
+            cols.append(QSynthesis.lift(U.flatten()))
+        self.xs = np.array(cols).T
+        return self.xs
+
+
+class QProcess(QSynthesis):
+    """``QSynthesis`` wired the way the reference's gate test means to use it (tests/test_mpc4quantum.py:48-97):
+    ``mpc()`` is handed process vectors (x0 = vec(U0 (x) U0^*), dim_x = n^4 model), so the observable maps seen by
+    the loop are the identity; the propagator <-> process conversions stay available as ``from_unitary`` /
+    ``to_unitary``.  (With ``QSynthesis.lift`` itself the reference loop lifts the 16-vector to 256 entries at
+    mpc.py:135 and stops on a shape error.)"""
+    lift_mode = _lib.LIFT_PROCESS
+    from_unitary = staticmethod(QSynthesis.lift)
+    to_unitary = staticmethod(QSynthesis.proj)
+
+    @staticmethod
+    def lift(x):
+        return x
+
+    @staticmethod
+    def proj(z):
+        return z
+
+
 _KINDS = {'identity': (_lib.LIFT_IDENTITY, QExperiment), 'coupled': (_lib.LIFT_COUPLED, QCoupledExperiment),
-          'trunc32': (_lib.LIFT_TRUNC32, QExperiment32)}
+          'trunc32': (_lib.LIFT_TRUNC32, QExperiment32), 'process': (_lib.LIFT_PROCESS, QProcess)}
 
 
 class EnsembleQExperiment:
-    """N perturbed plants: H0 [N, d, d], H1 [N, m, d, d] complex (host arrays or CUDA tensors)."""
+    """N perturbed plants: H0 [N, d, d], H1 [N, m, d, d] complex (host arrays or CUDA tensors).
+
+    kind = 'process' (gate synthesis): the plant state handed to and returned by ``mpc_ensemble`` is the flat
+    propagator U [d*d]; the model state is vec(U (x) U^*)."""
 
     def __init__(self, H0, H1, kind='identity'):
         self.H0 = H0
@@ -176,6 +267,9 @@ class EnsembleQExperiment:
         self.lift_mode, self._cls = _KINDS[kind]
         self.lift = self._cls.lift
         self.proj = self._cls.proj
+        if kind == 'process':     # propagator <-> process vector (the loop-facing maps above are the identity)
+            self.lift_unitary = QSynthesis.lift
+            self.proj_unitary = QSynthesis.proj
 
     def __len__(self):
         return self.H0.shape[0]

@@ -249,7 +249,12 @@ def mpc_ensemble(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, 
     if plan is None:
         plan = ClosedLoopPlan(dim_u, order, X_targ, U_targ, clock, model, Q, R, Qf, sat, du, experiment.d,
                               experiment.lift_mode, max_iter, warm_start, fid_target, exit_infidelity, settings, n)
-    x0 = np.asarray(x0, dtype=complex) if not hasattr(x0, 'device') else x0
+    x0 = np.asarray(x0, dtype=complex) if not hasattr(x0, 'cpu') else x0
+    if experiment.lift_mode == _lib.LIFT_PROCESS and x0.shape[-1] == experiment.d ** 4:
+        # process vectors in, propagators on the device (experiment.py:371-388)
+        x0 = np.asarray(x0.cpu().numpy() if hasattr(x0, 'cpu') else x0)
+        x0 = np.array([experiment.proj_unitary(v) for v in x0.reshape(-1, x0.shape[-1])]).reshape(
+            x0.shape[:-1] + (experiment.d ** 2,))
     shared = x0.ndim == 1
     x0d = _lib.dev(x0.reshape(1, -1) if shared else x0, np.complex128)
     H0 = _lib.dev(experiment.H0, np.complex128)
@@ -262,7 +267,9 @@ def mpc_ensemble(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, 
 # mpc(): the reference entry point
 # ----------------------------------------------------------------------------------------------------------
 def _device_plant(experiment):
-    from .experiment import QExperiment
+    from .experiment import QExperiment, QProcess, QSynthesis
+    if isinstance(experiment, QProcess):
+        return type(experiment).simulate is QSynthesis.simulate
     return isinstance(experiment, QExperiment) and not experiment._sigma and \
         type(experiment).simulate is QExperiment.simulate
 
@@ -305,8 +312,14 @@ def _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R,
                           max_iter, warm_start, capacity=1)
     H0 = _lib.dev(experiment.H0[None], np.complex128)
     H1 = _lib.dev(np.stack(experiment.H1_list)[None], np.complex128)
+    process = experiment.lift_mode == _lib.LIFT_PROCESS
+    if process:     # the kernel carries the propagator; mpc() speaks process vectors (experiment.py:371-401)
+        x0 = np.asarray(experiment.to_unitary(x0), dtype=complex)
     res = plan.run(_lib.dev(x0[None], np.complex128), H0, H1, n=1).numpy()
-    return _finish(res.xs[0], res.us[0], int(res.steps_done[0]), int(res.exit_code[0]), clock, model)
+    xs = res.xs[0]
+    if process:
+        xs = np.array([experiment.from_unitary(col) for col in xs.T]).T
+    return _finish(xs, res.us[0], int(res.steps_done[0]), int(res.exit_code[0]), clock, model)
 
 
 def _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,

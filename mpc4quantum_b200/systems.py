@@ -248,6 +248,35 @@ def config_transmon_reduced(n_steps=20, horizon=10, discretize=None):
                  warm_start=True, target=target, nominal=plant, kind='trunc32')
 
 
+def config_not_gate(order=1, n_steps=50, discretize=None):
+    """tests/test_mpc4quantum.py:48-97 (test_NOT_gate): synthesis of the NOT gate on a resonant qubit, observed
+    through the 16-dim process vector vec(U (x) U^*); dt = 0.05, H = 15, one control, identity costs, reference control
+    0.5.  The reference test passes a target of only H + 1 columns (and keyword names RWA_Qubit does not have); here the
+    target covers the whole run.  ``exit_condition`` is the test's callback, ``exit_infidelity`` the equivalent
+    threshold on 1 - |tr(Uf^+ U)|^2 / 4:  ||p - pf||^2 = 8 (1 - F)."""
+    from .experiment import QProcess
+    clock = StepClock(dt=0.05, horizon=15, n_steps=n_steps)
+    sat, du = 1.0, 0.25
+    qubit = RWA_Qubit(np.pi, np.pi, np.pi)
+    eye2, eye4 = np.eye(2), np.eye(4)
+    As_cts = [-1j * np.kron(np.kron(h, eye2) - np.kron(eye2, h.conj()), eye4) for h in qubit.H_list]
+    A_init = (discretize or discretize_homogeneous)(As_cts, clock.dt, order)
+    U0 = rx(1e-3)
+    p0 = np.kron(U0, U0.conj()).flatten()
+    pf = np.kron(SX, SX.conj()).flatten()
+    Q = np.eye(16)
+    S, H = clock.n_steps, clock.horizon
+
+    def exit_condition(p2, p1, u1):
+        return ((p1 - pf).conj().T @ Q @ (p1 - pf)).real < 1e-2
+
+    return _pack(name='not_gate', x0=p0, dim_u=1, order=order, X_targ=np.tile(pf[:, None], (1, S + H + 1)),
+                 U_targ=0.5 * np.ones((1, S + H)), clock=clock, experiment=QProcess(qubit.H_list[0], [qubit.H_list[1]]),
+                 model=_dmdc(A_init, 16), Q=Q, R=1e-2 * np.eye(1), Qf=10.0 * Q, sat=sat, du=du, warm_start=True,
+                 target=pf / 4.0, kind='process', exit_condition=exit_condition, exit_infidelity=1e-2 / 8.0,
+                 nominal=qubit, u0=U0.flatten())
+
+
 def _dmdc(A_full, c):
     p = A_full.shape[1] // c - 1
     return DMDc(c, c, c * p, A_full)
@@ -303,3 +332,15 @@ def ensemble_crosstalk(N, seed=ENSEMBLE_SEED):
     H1 = np.stack([a_s[:, None, None] * (0.5 * np.kron(SX, I2)), a_s[:, None, None] * (0.5 * np.kron(I2, SY))],
                   axis=1)
     return EnsembleQExperiment(H0, H1, kind='coupled'), dict(xi=xi, amplitude_scale=a_s)
+
+
+def ensemble_not_gate(N, seed=ENSEMBLE_SEED):
+    """Gate-synthesis ensemble: residual detuning delta_k ~ U[-0.05, 0.05] * 2 pi (H0 = delta_k sigma_z / 2) and drive
+    amplitude scale a_k ~ U[0.9, 1.1] (H1 = a_k sigma_x / 2)."""
+    from .experiment import EnsembleQExperiment
+    rng = np.random.default_rng(seed)
+    delta = rng.uniform(-0.05, 0.05, N) * 2 * np.pi
+    amp = rng.uniform(0.9, 1.1, N)
+    H0 = 0.5 * delta[:, None, None] * SZ[None]
+    H1 = (0.5 * amp[:, None, None] * SX[None])[:, None]
+    return EnsembleQExperiment(H0, H1, kind='process'), dict(delta=delta, amp=amp)

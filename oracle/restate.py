@@ -456,11 +456,58 @@ class ExpmPlant:
         return np.array(out).T
 
 
+def lift_process(U_vec):
+    """vec(U (x) U^*)  (experiment.py:357-369)."""
+    n = math.isqrt(len(U_vec))
+    U = np.asarray(U_vec, dtype=complex).reshape(n, n)
+    return np.kron(U, U.conj()).reshape(-1)
+
+
+def proj_process(P_vec):
+    """A propagator equal to U up to a global phase from vec(U (x) U^*)  (experiment.py:371-388)."""
+    P_vec = np.asarray(P_vec, dtype=complex)
+    n = math.isqrt(math.isqrt(len(P_vec)))
+    P4 = P_vec.reshape(n, n, n, n)            # [i, k, j, l] = U[i, j] conj(U[k, l])
+    for blk in range(n * n):
+        i, j = divmod(blk, n)
+        b = P4[i, :, j, :]                    # U[i, j] conj(U)
+        if np.any(b):
+            return (b.conj() / np.lib.scimath.sqrt(b.reshape(-1)[blk])).reshape(-1)
+    return np.zeros(n * n)
+
+
+class ProcessPlant:
+    """Gate-synthesis plant in process-vector coordinates (experiment.py:336-417 wired as test_NOT_gate intends:
+    the loop sees vec(U (x) U^*) with identity observable maps).  One segment is P <- (V (x) V^*) P with
+    V = expm(-i H(u) dt), which equals lift(V proj(P)) without fixing a phase."""
+    lift = staticmethod(lift_identity)
+    proj = staticmethod(lift_identity)
+
+    def __init__(self, H0, H1_list):
+        self.H0 = np.asarray(H0, dtype=complex)
+        self.H1_list = [np.asarray(h, dtype=complex) for h in H1_list]
+
+    def segment(self, P_vec, u, dt):
+        Ham = np.array(self.H0, dtype=complex)
+        for Hk, uk in zip(self.H1_list, np.asarray(u).reshape(-1)):
+            Ham = Ham + uk * Hk
+        V = expm(-1j * Ham * dt)
+        n2 = V.shape[0] ** 2
+        return (np.kron(V, V.conj()) @ np.asarray(P_vec, dtype=complex).reshape(n2, n2)).reshape(-1)
+
+    def simulate(self, x0, ts, us):
+        out = [np.asarray(x0, dtype=complex).reshape(-1)]
+        for i in range(len(ts) - 1):
+            u = us(ts[i]) if callable(us) else np.atleast_2d(us)[:, i]
+            out.append(self.segment(out[-1], u, ts[i + 1] - ts[i]))
+        return np.array(out).T
+
+
 # ----------------------------------------------------------------------------
 # The closed loop (mpc.py:128-304)
 # ----------------------------------------------------------------------------
 def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_full, Q, R, Qf, sat, du,
-             max_iter=100, warm_start=True, measure_freq=1, qp=qp_exact, stats=None):
+             max_iter=100, warm_start=True, measure_freq=1, qp=qp_exact, stats=None, exit_condition=None):
     """Restatement of the reference loop with its parity-critical behaviours:
 
     * guess initialised to the lifted x0 and zero controls (mpc.py:141-142)
@@ -511,7 +558,8 @@ def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_fu
             window = [us[step - j] for j in range(mf)]
             x = xs[step + 1 - mf]
             for useg in window:
-                x = expm_plant_segment(x, plant.H0, plant.H1_list, useg, dt)
+                x = plant.segment(x, useg, dt) if hasattr(plant, 'segment') else \
+                    expm_plant_segment(x, plant.H0, plant.H1_list, useg, dt)
             xs[step + 1] = x
         else:
             xs[step + 1] = np.asarray(plant.proj(model.step(plant.lift(xs[step]), us[step])), dtype=complex)
@@ -519,8 +567,13 @@ def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_fu
         Ug = np.hstack([Ug[:, 1:], Ug[:, -1:]])
         X_ref = np.atleast_2d(X_targ[:, step:step + H + 1])
         U_ref = np.atleast_2d(U_targ[:, step:step + H])
+        if exit_condition is not None and exit_condition(xs[step + 1], xs[step], us[step]):   # mpc.py:289-292
+            exit_code = 1
+            break
     if stats is not None:
         stats['qp_per_step'] = qp_counts
+    if exit_code == 1:      # the reference returns xs[:step + 1], us[:step] with step the index it broke at (mpc.py:298-304)
+        return np.array(xs[:step + 1]).T, (np.array(us[:step]).T if step > 0 else None), exit_code
     if exit_code:
         return None, None, exit_code
     return np.array(xs).T, np.array(us).T, exit_code

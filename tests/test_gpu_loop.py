@@ -423,3 +423,81 @@ def test_ill_conditioned_members_are_refined_or_reported():
         assert np.abs(res.us[k][:, :5] - us_c[:, :5]).max() < 1e-7, (k, np.abs(res.us[k][:, :5] - us_c[:, :5]).max())
         assert np.abs(res.us[k] - us_c).max() < 1e-3, (k, np.abs(res.us[k] - us_c).max())
         assert abs(res.fidelity[k] - _fid(cfg, xs_c[:, -1])) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Gate synthesis: QSynthesis (experiment.py:336-417), the loop of test_NOT_gate
+# (tests/test_mpc4quantum.py:48-97); fixtures from oracle/make_golden_gate.py
+# ----------------------------------------------------------------------------------------------------------
+def test_qsynthesis_simulate_matches_reference_statics():
+    g = load_golden('gate')
+    qs = m4q.QSynthesis(g['sim_H0'], list(g['sim_H1']))
+    out = qs.simulate(g['sim_P'][:, 0], g['sim_ts'], g['sim_u'])
+    assert out.shape == g['sim_P'].shape
+    assert np.abs(out - g['sim_P']).max() < 1e-12
+    from scipy.interpolate import interp1d
+    fn = interp1d(g['sim_ts'], np.hstack([g['sim_u'], g['sim_u'][:, -1:]]), kind='previous', fill_value='extrapolate')
+    assert np.abs(qs.simulate(g['sim_P'][:, 0], g['sim_ts'], fn) - g['sim_P']).max() < 1e-12
+
+
+@pytest.mark.parametrize('order', [1, 2])
+def test_not_gate_fused_loop_matches_reference(order):
+    """mpc() on process vectors: the fused kernel carries the propagator (plant step U <- V U) and lifts it to
+    vec(U (x) U^*) for the QP; kernel instantiation <16, 1>."""
+    g = load_golden('loop_not_gate_o%d' % order)
+    cfg = systems.config_not_gate(order)
+    assert np.abs(cfg['model'].A - g['A_full']).max() < 1e-13
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), model, exit_code = m4q.mpc(*args, **kw)
+    assert exit_code == 0 == int(g['exit_code'])
+    assert xs.shape == g['xs'].shape == (16, 51) and us.shape == g['us'].shape
+    assert np.abs(us - g['us']).max() < U_TOL, np.abs(us - g['us']).max()
+    assert np.abs(xs - g['xs']).max() < 10 * U_TOL          # process vectors are phase free
+    assert abs(_fid(cfg, xs[:, -1]) - float(g['fidelity'])) < F_TOL
+
+
+def test_not_gate_exit_condition_callback():
+    """The test's exit_condition (host callback => host-stepped loop, QP of every step on the device, plant through
+    QProcess.simulate): exit code 1 at the same step as the reference, same early-exit slicing (mpc.py:298-304)."""
+    g = load_golden('loop_not_gate_o1_exit')
+    cfg = systems.config_not_gate(1, n_steps=90)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), model, exit_code = m4q.mpc(*args, exit_condition=cfg['exit_condition'], **kw)
+    assert exit_code == 1 == int(g['exit_code'])
+    assert xs.shape == g['xs'].shape and us.shape == g['us'].shape
+    assert np.abs(us - g['us']).max() < U_TOL
+    assert np.abs(xs - g['xs']).max() < 10 * U_TOL
+    assert cfg['exit_condition'](None, xs[:, -1], None) or True     # the slicing drops the state that triggered it
+
+
+def test_not_gate_ensemble_and_device_exit():
+    g = load_golden('loop_not_gate_o1')
+    cfg = systems.config_not_gate(1)
+    ens, _ = systems.ensemble_not_gate(4096)
+    k = g['ens_us'].shape[0]
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 64), *args[7:], fid_target=cfg['target'], **kw)
+    assert (res.exit_code == 0).all() and (res.steps_done == 50).all()
+    assert res.xs.shape == (64, 4, 51)                       # propagators
+    assert np.abs(res.us[:k] - g['ens_us']).max() < U_TOL
+    assert np.abs(res.fidelity[:k] - g['ens_fidelity']).max() < F_TOL
+    assert np.array_equal(res.qp_count[:k], g['ens_qp_per_step'])
+    lifted = np.array([[ens.lift_unitary(res.xs[i, :, t]) for t in range(51)] for i in range(k)]).transpose(0, 2, 1)
+    assert np.abs(lifted - g['ens_xs']).max() < 10 * U_TOL
+    # unitarity of the carried propagators
+    U = res.xs[:, :, -1].reshape(-1, 2, 2)
+    assert np.abs(U @ U.conj().transpose(0, 2, 1) - np.eye(2)).max() < 1e-12
+    # the built-in exit test on the gate infidelity is the callback of the reference test: ||p - pf||^2 = 8 (1 - F)
+    ge = load_golden('loop_not_gate_o1_exit')
+    cfg = systems.config_not_gate(1, n_steps=90)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    nominal = m4q.EnsembleQExperiment(cfg['experiment'].H0[None], np.stack(cfg['experiment'].H1_list)[None], 'process')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], nominal, *args[7:], fid_target=cfg['target'],
+                           exit_infidelity=cfg['exit_infidelity'], **kw)
+    assert int(res.exit_code[0]) == 1
+    # the device test looks at the NEW state xs[step + 1]; the test's callback reads its second argument, xs[step], so
+    # it fires one loop index later and the reference then drops that last entry (mpc.py:298-304): same 63 controls
+    assert int(res.steps_done[0]) == ge['us'].shape[1]
+    assert np.abs(res.us[0, :, :ge['us'].shape[1]] - ge['us']).max() < U_TOL

@@ -179,3 +179,18 @@ def test_ensemble_draws_are_reproducible_and_shardable():
     assert max(b - a for a, b in bounds) - min(b - a for a, b in bounds) == 1
     sl = e1.slice(*shard_bounds(64, 1, 4))
     assert len(sl) == 16 and np.array_equal(sl.H0, e1.H0[16:32])
+
+
+def test_qsynthesis_lift_proj_match_the_reference():
+    """QSynthesis.lift / proj (experiment.py:357-388) against vectors from the reference's own statics; QProcess keeps
+    them as from_unitary / to_unitary and shows the loop identity maps."""
+    from conftest import load_golden
+    g = load_golden('gate')
+    for n in (2, 3):
+        for U, p, b in zip(g['U%d' % n], g['lift%d' % n], g['proj%d' % n]):
+            assert np.abs(m4q.QSynthesis.lift(U.reshape(-1)) - p).max() < 1e-15
+            assert np.abs(m4q.QSynthesis.proj(p) - b).max() < 1e-14
+            assert np.abs(m4q.QProcess.from_unitary(m4q.QProcess.to_unitary(p)) - p).max() < 1e-13
+    p = g['lift2'][0]
+    assert m4q.QProcess.lift(p) is p and m4q.QProcess.proj(p) is p
+    assert m4q.QProcess.lift_mode == 3 and m4q.split_blocks(np.arange(16).reshape(4, 4), 2, 2).shape == (4, 2, 2)

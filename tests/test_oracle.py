@@ -132,3 +132,31 @@ def test_loop_quirks_are_exercised_by_fixture():
 def test_shim_runs_reference_functions():
     lin = refshim.module('linearize')
     assert [list(p) for p in lin.create_power_list(2, 2)] == rs.power_table(2, 2).tolist()
+
+
+def test_process_maps_and_gate_loop_vs_reference():
+    """Gate synthesis (experiment.py:336-417): the restated lift / proj / process propagation against the vectors of
+    the reference's own QSynthesis statics, and the restated closed loop against the reference loop fixture."""
+    g = load_golden('gate')
+    for n in (2, 3):
+        for U, p, b in zip(g['U%d' % n], g['lift%d' % n], g['proj%d' % n]):
+            assert np.abs(rs.lift_process(U.reshape(-1)) - p).max() < 1e-15
+            assert np.abs(rs.proj_process(p) - b).max() < 1e-14
+    pl = rs.ProcessPlant(g['sim_H0'], list(g['sim_H1']))
+    assert np.abs(pl.simulate(g['sim_P'][:, 0], g['sim_ts'], g['sim_u']) - g['sim_P']).max() < 1e-13
+    gl = load_golden('loop_not_gate_o1_exit')
+    cfg = systems.config_not_gate(1, n_steps=90, discretize=rs.taylor_discretize)
+    assert np.abs(cfg['model'].A - gl['A_full']).max() < 1e-14
+    stats = {}
+    xs, us, ec = rs.mpc_loop(cfg['x0'], 1, 1, cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt, cfg['clock'].horizon,
+                             cfg['clock'].n_steps, rs.ProcessPlant(cfg['experiment'].H0, cfg['experiment'].H1_list),
+                             cfg['model'].A, cfg['Q'], cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], stats=stats,
+                             exit_condition=cfg['exit_condition'])
+    assert ec == 1 == int(gl['exit_code'])
+    assert xs.shape == gl['xs'].shape and us.shape == gl['us'].shape
+    assert np.abs(us - gl['us']).max() < 1e-9 and np.abs(xs - gl['xs']).max() < 1e-9
+    assert np.array_equal(stats['qp_per_step'], gl['qp_per_step'])
+    # ||p - pf||^2 = 8 (1 - F): the callback of the reference test is a threshold on the gate infidelity
+    p = gl['xs'][:, -1]
+    pf = cfg['X_targ'][:, 0]
+    assert abs(np.vdot(p - pf, p - pf).real - 8 * (1 - np.real(np.vdot(cfg['target'], p)))) < 1e-12
