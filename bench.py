@@ -33,10 +33,13 @@ SYSTEM_NAMES = {'transmon': '3-level transmon', 'qubit': 'ideal qubit', 'crossta
 
 def workload(name, discretize=None):
     from mpc4quantum_b200 import systems
-    if name.startswith('transmon_h') or name.startswith('transmon_o2_h'):
+    if name.startswith('transmon_h') or name.startswith('transmon_o2_h') or name.startswith('transmon_models_h'):
         order = 2 if name.startswith('transmon_o2_h') else 1
         H = int(name.split('_h')[-1])
-        return systems.config_transmon(order, horizon=H, n_steps=20, discretize=discretize), systems.ensemble_transmon
+        cfg = systems.config_transmon(order, horizon=H, n_steps=20, discretize=discretize)
+        # transmon_models_hH: every member also controls with its own perturbed MODEL (discretised per member)
+        cfg['per_member_models'] = name.startswith('transmon_models_h')
+        return cfg, systems.ensemble_transmon
     if name == 'qubit':
         return systems.config_qubit(1, discretize=discretize), systems.ensemble_qubit
     if name == 'crosstalk':
@@ -114,8 +117,13 @@ def _cpu_member(job):
     plant = rs.ProcessPlant(mem.H0, mem.H1_list) if cfg.get('kind') == 'process' else \
         rs.ExpmPlant(mem.H0, mem.H1_list, lift, proj)
     stats = {}
+    A_full = cfg['model'].A
+    if cfg.get('per_member_models'):
+        from mpc4quantum_b200 import systems
+        L, _ = systems.transmon_model_liouvillians(n_total)
+        A_full = rs.taylor_discretize(list(L[k]), cfg['clock'].dt, cfg['order'])
     xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
-                             cfg['clock'].horizon, cfg['clock'].n_steps, plant, cfg['model'].A, cfg['Q'], cfg['R'],
+                             cfg['clock'].horizon, cfg['clock'].n_steps, plant, A_full, cfg['Q'], cfg['R'],
                              cfg['Qf'], cfg['sat'], cfg['du'], warm_start=cfg['warm_start'],
                              measure_freq=cfg['clock'].measure_freq, stats=stats)
     return float(np.real(np.vdot(cfg['target'], xs[:, -1]))), int(sum(stats['qp_per_step']))
@@ -209,7 +217,11 @@ def main():
     n = hi - lo
     ens_all, _ = maker(n_total)                      # same seeded draw on every rank; each keeps its block
     ens = ens_all.slice(lo, hi)
-    margs = (cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'], cfg['model'], cfg['Q'], cfg['R'],
+    model = cfg['model']
+    if cfg.get('per_member_models'):
+        from mpc4quantum_b200 import systems
+        model = systems.ensemble_transmon_models(n_total, order=cfg['order'])[0].slice(lo, hi)
+    margs = (cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'], model, cfg['Q'], cfg['R'],
              cfg['Qf'], cfg['sat'], cfg['du'])
     plan = m4q.ClosedLoopPlan(*margs, d=ens.d, lift_mode=ens.lift_mode, warm_start=cfg['warm_start'],
                               fid_target=cfg['target'], capacity=n,

@@ -72,6 +72,9 @@ typedef struct {
     const double *U_targ;     /* [m][n_targ-1] real   (mpc.py:146, :277)                               */
     const double *fid_vec;    /* [d*d] complex or NULL: fidelity[k] = Re sum conj(fid_vec) * x_final   */
     m4q_qp_settings qp;
+    int32_t model_per_member; /* 0: A_blocks is one model shared by all members; 1: A_blocks is [N][p+1][c][c],
+                                 member k controls with its own (perturbed) model -- e.g. the output of
+                                 m4q_taylor_discretize_batched regrouped per block                           */
 } m4q_mpc_problem;
 
 int m4q_version(void);
@@ -83,7 +86,8 @@ int m4q_supported(int32_t c, int32_t m);
 /*
  * Plant step(s): rho <- U rho U^dagger, U = expm(-i (H0 + sum_k u_k H1_k) dt), n_seg consecutive segments.
  * Replaces QExperiment.simulate (experiment.py:202-212, qutip.mesolve) for the piecewise-constant control that
- * mpc.py:256-260 builds.  One warp per member.
+ * mpc.py:256-260 builds.  One thread per member with the matrices in registers (d <= 4, N >= 4096), else one warp
+ * per member.
  *   H0 [N][d][d] c128, H1 [N][m][d][d] c128 (member stride 0 allowed via h_stride_members = 0),
  *   u [N][n_seg][m] f64, rho_in [N][d*d] c128, rho_out [N][n_seg][d*d] c128 (state after each segment),
  *   prop_out [N][n_seg][d][d] c128 or NULL (the propagators, for the 1e-10 parity check).

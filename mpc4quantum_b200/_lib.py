@@ -28,7 +28,8 @@ class MpcProblem(ct.Structure):
                 ('measure_freq', c_i32), ('warm_start', c_i32), ('max_iter', c_i32), ('lift_mode', c_i32),
                 ('has_du', c_i32), ('n_targ', c_i32), ('dt', c_f64), ('sat', c_f64), ('du', c_f64),
                 ('exit_infidelity', c_f64), ('A_blocks', c_vp), ('powers', c_vp), ('Q', c_vp), ('Qf', c_vp),
-                ('R', c_vp), ('X_targ', c_vp), ('U_targ', c_vp), ('fid_vec', c_vp), ('qp', QPSettings)]
+                ('R', c_vp), ('X_targ', c_vp), ('U_targ', c_vp), ('fid_vec', c_vp), ('qp', QPSettings),
+                ('model_per_member', c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/m4q.h declares

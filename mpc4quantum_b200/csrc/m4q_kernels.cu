@@ -238,6 +238,7 @@ struct MpcArgs {
     double *state;
     double *ws;   // L2-resident workspaces, one per resident warp (ws_doubles<CF>(H) each)
     int slab_doubles, shared_doubles;
+    int model_per_member;   // A_blocks is [n_members][nblk][C][C]: every member controls with its own model
 };
 
 template <class CF>
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     double *Rr = Qfr + N * N;
     int *pow = reinterpret_cast<int *>(Rr + rup(M * M, 2));
 #pragma unroll 1
-    for (int e = threadIdx.x; e < a.nblk * C * C; e += blockDim.x) blocks[e] = a.A_blocks[e];
+    for (int e = threadIdx.x; e < a.nblk * C * C; e += blockDim.x) blocks[e] = a.model_per_member ? make_double2(0.0, 0.0) : a.A_blocks[e];
     for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
         Qr[e] = a.tab[L.Qr + e];
         Qfr[e] = a.tab[L.Qfr + e];
@@ -282,6 +283,11 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     model.nblk = a.nblk;
     model.stage_stride = 0;
     model.soff = 0;
+    if (a.model_per_member) {
+        // perturbed MODELS: the member's own blocks sit behind its slab (the slab stride includes them)
+        model.soff = sr.off + a.slab_doubles - 2 * a.nblk * C * C;
+        model.blocks = reinterpret_cast<const double2 *>(smem + model.soff);
+    }
 
     int *work = reinterpret_cast<int *>(a.tab + L.flags + 1);
     const int q_diag = a.tab[L.flags] != 0.0;
@@ -299,6 +305,13 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         double *us_k = a.us + (size_t)k * M * S;
         const double2 *H0k = a.H0 ? a.H0 + (a.shared_ham ? 0 : (size_t)k * dd) : nullptr;
         const double2 *H1k = a.H1 ? a.H1 + (a.shared_ham ? 0 : (size_t)k * M * dd) : nullptr;
+        if (a.model_per_member) {
+            double2 *mine = reinterpret_cast<double2 *>(smem + model.soff);
+            const double2 *src = a.A_blocks + (size_t)k * a.nblk * C * C;
+#pragma unroll 1
+            for (int e = lane; e < a.nblk * C * C; e += 32) mine[e] = src[e];
+            __syncwarp();
+        }
 
         // ---- initial or restored loop state
         if (a.step_begin == 0) {
@@ -1314,7 +1327,8 @@ template <class CF> static int mpc_shared_doubles(int nblk) {
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
     const int dd = p->d * p->d;
     if (!Slab<CF>::scratch_fits(p->p + 1, cmax(dd, CF::C))) return fail("model / plant too large for the slab scratch");
-    const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2);
+    const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2) +
+                     (p->model_per_member ? 2 * (p->p + 1) * CF::C * CF::C : 0);
     return plan(mpc_kernel<CF>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
 }
 
@@ -1656,6 +1670,7 @@ int m4q_mpc_closed_loop(const m4q_mpc_problem *p, int64_t N, const double *x0, i
     a.exit_infid = p->exit_infidelity;
     a.set = qp_settings(&p->qp);
     a.A_blocks = (const double2 *)p->A_blocks;
+    a.model_per_member = p->model_per_member != 0;
     a.powers = p->powers;
     a.fid_vec = (const double2 *)p->fid_vec;
     a.tab = (double *)tables;

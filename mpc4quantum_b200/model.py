@@ -165,3 +165,30 @@ class OnlineDMDc(DMDc, _History):
             self.iA.append(np.copy(self.A))
             self.iP.append(np.copy(self.P))
         return self.get_discrete()
+
+
+class DMDcEnsemble:
+    """N perturbed MODELS of one shape for ``mpc_ensemble``: member k controls with ``A[k]`` = [A_x | A_u] of its own
+    (additive to the reference API; one ``DMDc`` per member, model.py:11-31, without N Python objects).
+
+    ``A`` is a host array or CUDA tensor [N, dim_y, dim_x + dim_u], e.g. the output of
+    ``vectorize.discretize_homogeneous_batched`` for N sets of Liouvillians.
+    """
+
+    def __init__(self, dim_y, dim_x, dim_u, A):
+        self.dim_y, self.dim_x, self.dim_u = dim_y, dim_x, dim_u
+        self.A = A
+
+    def __len__(self):
+        return self.A.shape[0]
+
+    def member(self, k):
+        A = self.A[k]
+        return DMDc(self.dim_y, self.dim_x, self.dim_u, A.cpu().numpy() if hasattr(A, 'cpu') else np.asarray(A))
+
+    def slice(self, lo, hi):
+        return DMDcEnsemble(self.dim_y, self.dim_x, self.dim_u, self.A[lo:hi])
+
+    def get_discrete(self):
+        """Operators of member 0 (shape checks, library size)."""
+        return self.member(0).get_discrete()

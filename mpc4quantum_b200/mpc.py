@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _lib
 from .linearize import WrapModel, create_library, krtimes, model_blocks, size_of_library, create_power_list
+from .model import DMDcEnsemble
 
 
 class StepClock:
@@ -175,8 +176,17 @@ class ClosedLoopPlan:
         k = min(n_targ - 1, U_targ.shape[1])
         Ut[:, :k] = U_targ[:, :k]
         Ut[:, k:] = U_targ[:, k - 1:k]
+        per_member = isinstance(model, DMDcEnsemble)
+        if per_member:
+            # [N, c, c (p+1)] -> [N, p+1, c, c]: block 0 = A_x, block k = N_k of every member (linearize.py:32)
+            stack = _lib.dev(model.A, np.complex128)
+            blocks = stack.reshape(len(model), self.c, self.p + 1, self.c).permute(0, 2, 1, 3).contiguous()
+            self.n_models = len(model)
+        else:
+            blocks = _lib.dev(model_blocks(A_x, A_u), np.complex128)
+            self.n_models = 0
         self._keep = dict(
-            blocks=_lib.dev(model_blocks(A_x, A_u), np.complex128),
+            blocks=blocks,
             powers=_lib.dev(wrapped.powers, np.int32),
             Q=_lib.dev(np.asarray(Q, dtype=complex).reshape(self.c, self.c), np.complex128),
             Qf=_lib.dev(np.asarray(Qf, dtype=complex).reshape(self.c, self.c), np.complex128),
@@ -193,7 +203,7 @@ class ClosedLoopPlan:
             int(du is not None), n_targ, float(clock.dt), float(sat), float(du) if du is not None else 0.0,
             float(exit_infidelity), kp['blocks'].data_ptr(), kp['powers'].data_ptr(), kp['Q'].data_ptr(),
             kp['Qf'].data_ptr(), kp['R'].data_ptr(), kp['Xt'].data_ptr(), kp['Ut'].data_ptr(),
-            kp['fid'].data_ptr() if kp['fid'] is not None else None, st)
+            kp['fid'].data_ptr() if kp['fid'] is not None else None, st, int(per_member))
         tb = int(lib.m4q_mpc_table_bytes(ct.byref(self.prob)))
         if tb < 0:
             _lib.check(-1)
@@ -222,6 +232,8 @@ class ClosedLoopPlan:
             step_end=None, stream=None):
         """Enqueue the closed loop for n members.  x0/H0/H1 are CUDA tensors (complex128)."""
         n = self.capacity if n is None else int(n)
+        if self.n_models and n > self.n_models:
+            raise ValueError('%d members but only %d models' % (n, self.n_models))
         if n > self.capacity:
             self._alloc(n)
         step_end = self.S if step_end is None else step_end

@@ -344,3 +344,30 @@ def ensemble_not_gate(N, seed=ENSEMBLE_SEED):
     H0 = 0.5 * delta[:, None, None] * SZ[None]
     H1 = (0.5 * amp[:, None, None] * SX[None])[:, None]
     return EnsembleQExperiment(H0, H1, kind='process'), dict(delta=delta, amp=amp)
+
+
+def transmon_model_liouvillians(N, seed=ENSEMBLE_SEED + 1, dt=0.25):
+    """Perturbed controller MODELS for the transmon (pure numpy): member k believes in the anharmonicity
+    k_k alpha, k_k ~ U[0.95, 1.05], and in drive amplitudes scaled by g_k ~ U[0.97, 1.03].
+    Returns the Liouvillians L [N, 3, 9, 9] of [H0, HX, HY] per member (row-major vec(rho)) and the draws."""
+    rng = np.random.default_rng(seed)
+    k = rng.uniform(0.95, 1.05, N)
+    g = rng.uniform(0.97, 1.03, N)
+    alpha = -2 * np.pi * 0.1 / dt
+    a = destroy(3)
+    H = np.stack([(k * alpha)[:, None, None] * proj(3, 2)[None],
+                  g[:, None, None] * (0.5 * (a.conj().T + a))[None],
+                  g[:, None, None] * (0.5j * (a.conj().T - a))[None]], axis=1)          # [N, 3, 3, 3]
+    eye = np.eye(3)
+    L = -1j * (np.einsum('nkab,cd->nkacbd', H, eye) - np.einsum('ab,nkdc->nkacbd', eye, H)).reshape(N, 3, 9, 9)
+    return L, dict(model_anharm_scale=k, model_amplitude_scale=g)
+
+
+def ensemble_transmon_models(N, order=1, dt=0.25, seed=ENSEMBLE_SEED + 1):
+    """The N perturbed models discretised on the device (m4q_taylor_discretize_batched, vectorize.py:8-49 per member)
+    as a ``DMDcEnsemble`` for ``mpc_ensemble``."""
+    from .model import DMDcEnsemble
+    from .vectorize import discretize_homogeneous_batched
+    L, params = transmon_model_liouvillians(N, seed, dt)
+    A = discretize_homogeneous_batched(L, dt, order)
+    return DMDcEnsemble(9, 9, A.shape[2] - 9, A), params

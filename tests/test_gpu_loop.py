@@ -501,3 +501,40 @@ def test_not_gate_ensemble_and_device_exit():
     # it fires one loop index later and the reference then drops that last entry (mpc.py:298-304): same 63 controls
     assert int(res.steps_done[0]) == ge['us'].shape[1]
     assert np.abs(res.us[0, :, :ge['us'].shape[1]] - ge['us']).max() < U_TOL
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Ensembles of perturbed MODELS: every member controls with its own model blocks (m4q_mpc_problem.model_per_member),
+# discretised per member on the device; fixture = the reference's mpc() run once per member (oracle/make_golden_models.py)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('order', [1, 2])
+def test_per_member_models_match_reference_runs(order):
+    g = load_golden('loop_transmon_models')
+    cfg = systems.config_transmon(order)
+    k = g['o%d_us' % order].shape[0]
+    plants, _ = systems.ensemble_transmon(65536)
+    models, params = systems.ensemble_transmon_models(65536, order=order)
+    # the batched device discretisation of the perturbed models == the reference's discretize_homogeneous per member
+    A_dev = models.A[:k].cpu().numpy()
+    assert np.abs(A_dev - g['o%d_A' % order]).max() < 1e-13
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    n = 96                                                     # more members than fit one wave of one SM's warps
+    res = m4q.mpc_ensemble(args[0], *args[1:6], plants.slice(0, n), models.slice(0, n), *args[8:],
+                           fid_target=cfg['target'], **kw)
+    assert (res.exit_code == 0).all()
+    tol_u = np.maximum(U_TOL, 20 * g['o%d_us_sensitivity' % order])
+    tol_f = np.maximum(F_TOL, 20 * g['o%d_fid_sensitivity' % order])
+    du = np.abs(res.us[:k] - g['o%d_us' % order]).reshape(k, -1).max(axis=1)
+    df = np.abs(res.fidelity[:k] - g['o%d_fidelity' % order])
+    assert (du < tol_u).all(), (du, tol_u)
+    assert (df < tol_f).all(), (df, tol_f)
+    assert np.abs(res.us[:k, :, :3] - g['o%d_us' % order][:, :, :3]).max() < 1e-7
+    assert np.array_equal(res.qp_count[:k], g['o%d_qp_per_step' % order])
+    # each member alone through mpc() with its own DMDc (shared-model path) gives the same trajectory bit for bit
+    for i in (1, 70):
+        (xs, us), _, ec = m4q.mpc(args[0], *args[1:6], plants.member(i), models.member(i), *args[8:], **kw)
+        assert ec == 0 and np.array_equal(us, res.us[i]) and np.array_equal(xs, res.xs[i])
+    # and the perturbed models matter: the nominal model on the same plants gives different controls
+    nominal = m4q.mpc_ensemble(args[0], *args[1:6], plants.slice(0, k), *args[7:], fid_target=cfg['target'], **kw)
+    assert np.abs(nominal.us - res.us[:k]).max() > 1e-3

@@ -32,13 +32,30 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.QPSettings) == 40
-    assert ctypes.sizeof(_lib.MpcProblem) == 12 * 4 + 4 * 8 + 8 * 8 + 40
+    assert ctypes.sizeof(_lib.MpcProblem) == 12 * 4 + 4 * 8 + 8 * 8 + 40 + 8        # + model_per_member, padded
     assert _lib.MpcProblem.dt.offset == 48 and _lib.MpcProblem.A_blocks.offset == 80
+    assert _lib.MpcProblem.model_per_member.offset == 184
+    assert lib_sizeof_problem() == ctypes.sizeof(_lib.MpcProblem)
+
+
+def lib_sizeof_problem():
+    """sizeof(m4q_mpc_problem) as the C compiler lays it out (gcc on the header)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, 's.c')
+        with open(src, 'w') as f:
+            f.write('#include <stdio.h>\n#include "m4q.h"\nint main(void){printf("%zu", sizeof(m4q_mpc_problem));return 0;}\n')
+        exe = os.path.join(tmp, 's')
+        subprocess.check_call(['gcc', '-I', os.path.join(root, 'include'), src, '-o', exe])
+        return int(subprocess.check_output([exe]))
 
 
 def test_supported_instantiations_and_argument_errors():
     lib = _lib.lib()
     assert lib.m4q_supported(9, 2) and lib.m4q_supported(4, 1) and lib.m4q_supported(8, 2) and lib.m4q_supported(16, 3)
+    assert lib.m4q_supported(16, 1) and lib.m4q_supported(4, 2)
     assert not lib.m4q_supported(5, 1)
     prob = _lib.MpcProblem(c=5, m=1, p=1, d=2, horizon=4, n_steps=2, measure_freq=1, n_targ=7, sat=1.0)
     assert lib.m4q_mpc_table_bytes(ctypes.byref(prob)) == -1
@@ -53,6 +70,12 @@ def test_launch_geometry_without_a_device():
     w, c, s = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
     assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
     assert 1 <= w.value <= 16 and c.value % 148 == 0 and s.value <= 227 * 1024
+    shared_w, shared_s = w.value, s.value
+    prob.model_per_member = 1   # every warp also holds its member's model blocks: 3 * 81 complex more per warp
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert 1 <= w.value <= shared_w and s.value <= 227 * 1024
+    assert (s.value / w.value) - (shared_s / shared_w) > 0.9 * 3 * 81 * 16
+    prob.model_per_member = 0
     prob.horizon = 400          # does not fit the shared-memory slab: refused, not truncated
     assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == -1
 
