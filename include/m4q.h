@@ -117,6 +117,16 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
                           double *A_out, double *B_out, double *D_out, void *stream);
 
 /*
+ * Exact-discretisation model mode (no counterpart in the reference, whose model is the order-k Taylor expansion of
+ * vectorize.py:8-49): x+ = expm(G(u) dt) x with the continuous-time generators G(u) = L_0 + sum_i u_i L_i.
+ *   A_t = expm(G(u_t) dt), B_t[:, i] = d/du_i [expm(G(u) dt)] x_t (Frechet derivative applied to x_t),
+ *   Delta_t = -B_t u_t.  generators [m+1][c][c] c128 (shared by all instances); other layouts as above.
+ */
+int m4q_exact_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t H, double dt, const double *generators,
+                                const double *Xg, const double *Ug,
+                                double *A_out, double *B_out, double *D_out, void *stream);
+
+/*
  * Horizon QP.  Replaces optimize.quad_program (optimize.py:12-60; cvxpy -> OSQP):
  *   min sum_t Re[(x_t-r_t)^H Q_t (x_t-r_t)] + (u_t-ub_t)^T R_t (u_t-ub_t) + terminal
  *   s.t. x_0 = x_init, x_{t+1} = Delta_t + A_t x_t + B_t u_t, |u_t| <= sat, |u_0 - u_prev| <= du.

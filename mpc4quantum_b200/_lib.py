@@ -42,6 +42,7 @@ SIGNATURES = {
     'm4q_taylor_discretize_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32, c_i32, c_f64, c_vp, c_vp, c_vp, c_vp]),
     'm4q_linearize_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                          c_vp]),
+    'm4q_exact_linearize_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32, c_f64] + [c_vp] * 7),
     'm4q_qp_workspace_bytes': (c_i64, [c_i64, c_i32, c_i32, c_i32]),
     'm4q_qp_admm_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32] + [c_vp] * 9 + [c_f64, c_f64, c_i32,
                                        ct.POINTER(QPSettings)] + [c_vp] * 7),

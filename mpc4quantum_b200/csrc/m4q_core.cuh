@@ -1541,6 +1541,152 @@ __device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, do
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Exact discretisation of the bilinear generator (replaces the Taylor blocks of
+// vectorize.py:8-49 for this model mode):  x+ = expm(G(u) dt) x,  G(u) = L_0 + sum_i u_i L_i.
+//   A = expm(G dt)                      scaling and squaring of a degree-16 Taylor polynomial, C x C complex
+//   b_i = (d/du_i expm(G(u) dt)) x      = w_i(1) of  y' = G dt y,  w_i' = G dt w_i + L_i dt y,  y(0) = x, w_i(0) = 0,
+//                                       integrated exactly by Taylor series on sub-steps of norm <= 2
+// gen [M+1][C][C] (shared or global), u [M], x [C] (shared).  scr: double2 [exact_scratch<CF>()] shared.
+// On return A sits in scr[C*C .. 2*C*C) and b_i[r] in scr[exact_b_offset<CF>() + i*C + r].  All lanes must call.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF> __host__ __device__ constexpr int exact_b_offset() { return 2 * CF::C * CF::C + 2 * (1 + CF::M) * CF::C; }
+template <class CF> __host__ __device__ constexpr int exact_scratch() { return exact_b_offset<CF>() + CF::M * CF::C; }
+
+template <class CF>
+__device__ __noinline__ void exact_stage(const double2 *gen, const double *u, const double2 *x, double dt, double2 *scr,
+                                         int lane) {
+    constexpr int C = CF::C, M = CF::M, CC = C * C, NE = cdiv(CC, 32), NV = cdiv((1 + M) * C, 32);
+    double2 *G = scr, *T = scr + CC, *vec = scr + 2 * CC, *bout = scr + exact_b_offset<CF>();
+    // ---- G = dt (L_0 + sum u_i L_i), 1-norm
+    double uu[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) uu[i] = u[i];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+        const int e = lane + 32 * q;
+        if (e < CC) {
+            double2 g = gen[e];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double2 l = gen[(1 + i) * CC + e];
+                g.x = fma(uu[i], l.x, g.x);
+                g.y = fma(uu[i], l.y, g.y);
+            }
+            G[e] = make_double2(g.x * dt, g.y * dt);
+        }
+    }
+    __syncwarp();
+    double nrm = 0.0;
+    if (lane < C) {
+#pragma unroll 1
+        for (int i = 0; i < C; ++i) {
+            const double2 g = G[i * C + lane];
+            nrm += hypot(g.x, g.y);
+        }
+    }
+    nrm = warp_max(nrm);
+    const double theta = nrm;
+    int sq = 0;
+    while (nrm > 0.5 && sq < 40) {
+        nrm *= 0.5;
+        ++sq;
+    }
+    const double sc = ldexp(1.0, -sq);
+    // ---- T = expm(G): Horner of degree 16 on G / 2^sq, then sq squarings.  Each lane owns entries lane + 32 q.
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+        const int e = lane + 32 * q;
+        if (e < CC) T[e] = make_double2(e / C == e % C ? 1.0 : 0.0, 0.0);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 16 + sq; k >= 1; --k) {
+        const bool horner = k > sq;                      // first 16 passes: T = I + (sc / kk) G T; then T = T T
+        const double f = horner ? sc / (double)(k - sq) : 1.0;
+        const double2 *Lm = horner ? G : T;
+        double2 v[NE];
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+            const int e = lane + 32 * q;
+            const int ec = e < CC ? e : CC - 1;
+            const int i = ec / C, j = ec % C;
+            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk) {
+                if (kk & 1) a1 = cfma(Lm[i * C + kk], T[kk * C + j], a1);
+                else a0 = cfma(Lm[i * C + kk], T[kk * C + j], a0);
+            }
+            v[q] = make_double2(fma(a0.x + a1.x, f, (horner && i == j) ? 1.0 : 0.0), (a0.y + a1.y) * f);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+            const int e = lane + 32 * q;
+            if (e < CC) T[e] = v[q];
+        }
+        __syncwarp();
+    }
+    // ---- b_i: Taylor series of the augmented vector system on n_sub sub-steps (||G|| / n_sub <= 2, 26 terms)
+    int n_sub = (theta < 128.0) ? (int)ceil(theta * 0.5) : 64;     // also catches a non-finite generator
+    if (n_sub < 1) n_sub = 1;
+    const double h = 1.0 / (double)n_sub;
+    // vec: two buffers [(1 + M) C]: term vectors (y-term, w_1-term, ...); lane job e -> (v = e / C, r = e % C)
+    double2 acc[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int e = lane + 32 * q;
+        acc[q] = (e < C) ? x[e] : make_double2(0.0, 0.0);
+        if (e < (1 + M) * C) vec[e] = acc[q];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int sub = 0; sub < n_sub; ++sub) {
+        int cur = 0;
+#pragma unroll 1
+        for (int k = 1; k <= 26; ++k) {
+            const double f = h / (double)k;
+            const double2 *tv = vec + cur * (1 + M) * C;
+            double2 *nv = vec + (cur ^ 1) * (1 + M) * C;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int e = lane + 32 * q;
+                if (e < (1 + M) * C) {
+                    const int v = e / C, r = e % C;
+                    double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+                    const double2 *grow = G + r * C, *tw = tv + v * C;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) a0 = cfma(grow[j], tw[j], a0);
+                    if (v > 0) {
+                        const double2 *lrow = gen + v * CC + r * C;
+#pragma unroll
+                        for (int j = 0; j < C; ++j) a1 = cfma(lrow[j], tv[j], a1);
+                    }
+                    const double2 t = make_double2(fma(a1.x, dt, a0.x) * f, fma(a1.y, dt, a0.y) * f);
+                    nv[e] = t;
+                    acc[q].x += t.x;
+                    acc[q].y += t.y;
+                }
+            }
+            __syncwarp();
+            cur ^= 1;
+        }
+        // restart the series from the state at the end of the sub-step
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int e = lane + 32 * q;
+            if (e < (1 + M) * C) vec[e] = acc[q];
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int e = lane + 32 * q;
+        if (e >= C && e < (1 + M) * C) bout[e - C] = acc[q];
+    }
+    __syncwarp();
+}
+
 // U <- T U (gate synthesis: the plant state is the propagator itself, experiment.py:371-401)
 __device__ __noinline__ void left_multiply(double2 *U, const double2 *T, int d, double2 *tmp, int lane) {
     const bool act = lane < d * d;

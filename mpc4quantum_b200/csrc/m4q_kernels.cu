@@ -895,6 +895,62 @@ __global__ void __launch_bounds__(256) linearize_stage_kernel(const LinArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Stand-alone EXACT linearisation (model mode of SURVEY 8f rank 1): A_t = expm(G(u_t) dt), B_t = d/du [expm(G dt)] x_t,
+// Delta_t = -B_t u_t.  One warp per (instance, stage); generators shared by the CTA.
+// ---------------------------------------------------------------------------------------------------------
+struct ExactArgs {
+    long long n_inst;
+    int H;
+    double dt;
+    const double2 *gen;   // [M+1][C][C]
+    const double2 *Xg;
+    const double *Ug;
+    double2 *A_out, *B_out, *D_out;
+};
+
+template <class CF> __host__ __device__ inline int exact_warp_complex() { return exact_scratch<CF>() + CF::C + cdiv(CF::M, 2); }
+
+template <class CF>
+__global__ void __launch_bounds__(128) exact_linearize_kernel(const ExactArgs a) {
+    constexpr int C = CF::C, M = CF::M, CC = C * C;
+    extern __shared__ double2 smem2[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int H = a.H;
+    double2 *gen = smem2;
+    double2 *scr = smem2 + (M + 1) * CC + (size_t)warp * exact_warp_complex<CF>();
+    double2 *xs = scr + exact_scratch<CF>();
+    double *ut = reinterpret_cast<double *>(xs + C);
+#pragma unroll 1
+    for (int e = threadIdx.x; e < (M + 1) * CC; e += blockDim.x) gen[e] = a.gen[e];
+    __syncthreads();
+    const long long total = a.n_inst * H;
+#pragma unroll 1
+    for (long long item = (long long)blockIdx.x * wpc + warp; item < total; item += (long long)gridDim.x * wpc) {
+        const long long k = item / H;
+        const int t = (int)(item - k * H);
+        if (lane < C) xs[lane] = a.Xg[(size_t)k * C * (H + 1) + lane * (H + 1) + t];
+        if (lane < M) ut[lane] = a.Ug[(size_t)k * M * H + lane * H + t];
+        __syncwarp();
+        exact_stage<CF>(gen, ut, xs, a.dt, scr, lane);
+        const double2 *T = scr + CC, *b = scr + exact_b_offset<CF>();
+#pragma unroll 1
+        for (int e = lane; e < CC; e += 32) a.A_out[(size_t)item * CC + e] = T[e];
+#pragma unroll 1
+        for (int e = lane; e < C * M; e += 32) a.B_out[(size_t)item * C * M + e] = b[(e % M) * C + e / M];
+        if (lane < C) {
+            double2 d = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                d.x = fma(-b[i * C + lane].x, ut[i], d.x);
+                d.y = fma(-b[i * C + lane].y, ut[i], d.y);
+            }
+            a.D_out[(size_t)item * C + lane] = d;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Stand-alone line search (mpc.py:101-125); costs and references shared by all instances.
 // Workspace (doubles): Q [(H+1) N N] | R [H M M] | r [(H+1) N] | ub [H M]
 // ---------------------------------------------------------------------------------------------------------
@@ -1508,6 +1564,37 @@ int m4q_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t p, int32_t H,
         long long ctas = (N * H + wpc - 1) / wpc;
         if (ctas > 148LL * per_sm) ctas = 148LL * per_sm;
         linearize_stage_kernel<CF><<<(int)ctas, wpc * 32, smem, (cudaStream_t)stream>>>(a);
+    });
+    M4Q_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int m4q_exact_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t H, double dt, const double *generators,
+                                const double *Xg, const double *Ug, double *A_out, double *B_out, double *D_out,
+                                void *stream) {
+    if (N <= 0) return 0;
+    if (H < 1) return fail("exact linearize: horizon out of range");
+    if (!generators || !Xg || !Ug || !A_out || !B_out || !D_out) return fail("null pointer");
+    ExactArgs a;
+    a.n_inst = N;
+    a.H = H;
+    a.dt = dt;
+    a.gen = (const double2 *)generators;
+    a.Xg = (const double2 *)Xg;
+    a.Ug = Ug;
+    a.A_out = (double2 *)A_out;
+    a.B_out = (double2 *)B_out;
+    a.D_out = (double2 *)D_out;
+    M4Q_DISPATCH(c, m, {
+        const int wpc = 4;
+        const size_t smem = ((size_t)(m + 1) * c * c + (size_t)wpc * exact_warp_complex<CF>()) * sizeof(double2);
+        M4Q_CUDA(cudaFuncSetAttribute(exact_linearize_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        M4Q_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exact_linearize_kernel<CF>, wpc * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long ctas = (N * H + wpc - 1) / wpc;
+        if (ctas > 148LL * per_sm) ctas = 148LL * per_sm;
+        exact_linearize_kernel<CF><<<(int)ctas, wpc * 32, smem, (cudaStream_t)stream>>>(a);
     });
     M4Q_CUDA(cudaGetLastError());
     return 0;

@@ -192,3 +192,45 @@ class DMDcEnsemble:
     def get_discrete(self):
         """Operators of member 0 (shape checks, library size)."""
         return self.member(0).get_discrete()
+
+
+class ExactModel:
+    """Exact-discretisation model mode (no counterpart in the reference, whose models
+    are the order-k Taylor blocks of vectorize.py:8-49):  x+ = expm((L_0 + sum_i u_i L_i) dt) x.
+
+    ``generators`` = [L_0, L_1, ..., L_m], continuous-time c x c matrices (e.g. Liouvillians from ``vectorize_me``).
+    Handed to ``mpc`` / ``mpc_ensemble`` in place of a ``DMDc`` (``order`` is then ignored): the linearisation along
+    the guess is A_t = expm(G(u_t) dt), B_t = the Frechet derivative of that exponential applied to x_t, Delta_t = -B_t u_t,
+    evaluated on the device (``m4q_exact_linearize_batched`` stand-alone, inlined in the fused loop).
+    """
+
+    def __init__(self, generators, dt):
+        self.generators = np.stack([np.asarray(g, dtype=complex) for g in generators])
+        self.dt = float(dt)
+        self.dim_x = self.dim_y = self.generators.shape[1]
+        self.dim_u = self.generators.shape[0] - 1
+
+    def get_model_along_traj(self, xs, us, ts=None):
+        """xs [c, >= H+1], us [m, H] -> lists (A_t, B_t, Delta_t) like WrapModel.get_model_along_traj (linearize.py:61-70)."""
+        from . import _lib
+        us = np.atleast_2d(np.real(np.asarray(us)))
+        H = us.shape[1]
+        A, B, D = self._along(np.asarray(xs, dtype=complex)[None, :, :H + 1], us[None], H)
+        return list(A[0].cpu().numpy()), list(B[0].cpu().numpy()), [d.reshape(-1, 1) for d in D[0].cpu().numpy()]
+
+    def _along(self, xs, us, H):
+        from . import _lib
+        lib = _lib.lib()
+        c, m = self.dim_x, self.dim_u
+        if not lib.m4q_supported(c, m):
+            raise NotImplementedError('no compiled kernel for (dim_x, dim_u) = (%d, %d)' % (c, m))
+        Xg = _lib.dev(xs, np.complex128)
+        Ug = _lib.dev(np.real(us), np.float64)
+        nb = Xg.shape[0]
+        gen = _lib.dev(self.generators, np.complex128)
+        A_out = _lib.empty((nb, H, c, c), np.complex128)
+        B_out = _lib.empty((nb, H, c, m), np.complex128)
+        D_out = _lib.empty((nb, H, c), np.complex128)
+        _lib.check(lib.m4q_exact_linearize_batched(nb, c, m, H, self.dt, _lib.ptr(gen), _lib.ptr(Xg), _lib.ptr(Ug),
+                                                   _lib.ptr(A_out), _lib.ptr(B_out), _lib.ptr(D_out), _lib.stream_ptr()))
+        return A_out, B_out, D_out

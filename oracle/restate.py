@@ -154,6 +154,38 @@ class BilinearModel:
 # ----------------------------------------------------------------------------
 # Horizon QP (optimize.py:12-60)
 # ----------------------------------------------------------------------------
+class ExactModel:
+    """Exact-discretisation model (an extension, no reference counterpart):
+    x+ = expm(G(u) dt) x, G(u) = L_0 + sum u_i L_i.  A_t = expm(G dt); B_t[:, i] = L_expm(G dt, L_i dt) x_t with scipy's
+    Frechet derivative; Delta_t = f - A_t x_t - B_t u_t = -B_t u_t.  Same interface as BilinearModel."""
+
+    def __init__(self, generators, dt):
+        self.gen = [np.asarray(g, dtype=complex) for g in generators]
+        self.dt = dt
+        self.dim_u = len(self.gen) - 1
+
+    def _G(self, u):
+        G = np.array(self.gen[0])
+        for Li, ui in zip(self.gen[1:], np.asarray(u).reshape(-1)):
+            G = G + ui * Li
+        return G * self.dt
+
+    def step(self, x, u):
+        return expm(self._G(u)) @ x
+
+    def along(self, Xg, Ug, H):
+        from scipy.linalg import expm_frechet
+        A_ls, B_ls, D_ls = [], [], []
+        for t in range(H):
+            G = self._G(Ug[:, t])
+            A = expm(G)
+            B = np.stack([expm_frechet(G, Li * self.dt, compute_expm=False) @ Xg[:, t] for Li in self.gen[1:]], axis=1)
+            A_ls.append(A)
+            B_ls.append(B)
+            D_ls.append(-B @ Ug[:, t])
+        return A_ls, B_ls, D_ls
+
+
 def realify_vec(z):
     return np.concatenate([np.real(z), np.imag(z)])     # mpc.py:87-89
 
@@ -507,7 +539,7 @@ class ProcessPlant:
 # The closed loop (mpc.py:128-304)
 # ----------------------------------------------------------------------------
 def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_full, Q, R, Qf, sat, du,
-             max_iter=100, warm_start=True, measure_freq=1, qp=qp_exact, stats=None, exit_condition=None):
+             max_iter=100, warm_start=True, measure_freq=1, qp=qp_exact, stats=None, exit_condition=None, model=None):
     """Restatement of the reference loop with its parity-critical behaviours:
 
     * guess initialised to the lifted x0 and zero controls (mpc.py:141-142)
@@ -519,7 +551,7 @@ def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_fu
     Returns xs [dim, S+1], us [m, S], exit_code, and fills stats['qp_per_step'].
     """
     H, S, mf = horizon, n_steps, measure_freq
-    model = BilinearModel(A_full, dim_u, order)
+    model = model if model is not None else BilinearModel(A_full, dim_u, order)
     lx0 = np.asarray(plant.lift(np.asarray(x0, dtype=complex)), dtype=complex)
     Xg = np.tile(lx0.reshape(-1, 1), (1, H + 1))
     Ug = np.zeros((dim_u, H))

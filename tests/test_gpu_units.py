@@ -218,3 +218,44 @@ def test_quad_program_random_instances_all_instantiations(c, m):
                 n_active = int((np.abs(Uc - lo) < 1e-9).sum() + (np.abs(Uc - hi) < 1e-9).sum())
                 assert 0 <= n_active <= U.size
     assert worst < 1e-8
+
+
+@pytest.mark.parametrize('tag', ['qubit', 'transmon', 'coupled'])
+def test_exact_linearisation_vs_scipy_frechet(unit_golden, tag):
+    """Exact-discretisation model mode: A_t = expm(G(u_t) dt) within 1e-10 of scipy.linalg.expm (north_star), and
+    B_t = d/du expm(G dt) x_t against scipy.linalg.expm_frechet and a central finite difference."""
+    from scipy.linalg import expm
+    from oracle import restate as rs
+    L = list(unit_golden['disc_%s_L' % tag])
+    dt = float(unit_golden['disc_%s_dt' % tag])
+    c, m = L[0].shape[0], len(L) - 1
+    H = 12
+    rng = np.random.default_rng(21)
+    X = rng.normal(size=(c, H + 1)) + 1j * rng.normal(size=(c, H + 1))
+    U = rng.uniform(-2.0, 2.0, size=(m, H))          # generator norms up to ~6: several sub-steps and squarings
+    U[:, 0] = 0.0
+    model = m4q.ExactModel(L, dt)
+    A, B, D = model.get_model_along_traj(X, U)
+    A2, B2, D2 = rs.ExactModel(L, dt).along(X, U, H)
+    scale = max(1.0, np.abs(X).max())
+    assert np.abs(np.array(A) - np.array(A2)).max() < 1e-12
+    assert np.abs(np.array(B) - np.array(B2)).max() < 1e-11 * scale
+    assert np.abs(np.array(D)[:, :, 0] - np.array(D2)).max() < 1e-11 * scale * 2
+    # independent of scipy's Frechet routine: central difference of expm
+    t, eps = 5, 1e-6
+    for i in range(m):
+        e = np.zeros(m)
+        e[i] = eps
+        G = lambda u: (L[0] + sum(uk * Lk for uk, Lk in zip(u, L[1:]))) * dt
+        fd = (expm(G(U[:, t] + e)) - expm(G(U[:, t] - e))) @ X[:, t] / (2 * eps)
+        assert np.abs(B[t][:, i] - fd).max() < 1e-7 * scale
+    # consistency with the reference's Taylor model: the order-3 blocks agree with the exact map to O(dt^4)
+    if tag == 'qubit':
+        return
+    A_full = unit_golden['disc_%s_o3' % tag] if ('disc_%s_o3' % tag) in unit_golden else None
+    if A_full is not None:
+        bm = rs.BilinearModel(A_full, m, 3)
+        u_small = 0.1 * U[:, 3]
+        A_t = bm.jac_x(u_small)
+        A_e = expm((L[0] + sum(uk * Lk for uk, Lk in zip(u_small, L[1:]))) * dt)
+        assert np.abs(A_t - A_e).max() < 5e-2
