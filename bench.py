@@ -28,7 +28,8 @@ UNIT = 'trajectories/s'
 
 # ----------------------------------------------------------------------------------------------------------
 SYSTEM_NAMES = {'transmon': '3-level transmon', 'qubit': 'ideal qubit', 'crosstalk': 'two qubits with ZZ crosstalk',
-                'not_gate': 'NOT-gate synthesis on the qubit process vector'}
+                'not_gate': 'NOT-gate synthesis on the qubit process vector',
+                'transmon_exact': '3-level transmon, exact-discretisation model'}
 
 
 def workload(name, discretize=None):
@@ -40,6 +41,8 @@ def workload(name, discretize=None):
         # transmon_models_hH: every member also controls with its own perturbed MODEL (discretised per member)
         cfg['per_member_models'] = name.startswith('transmon_models_h')
         return cfg, systems.ensemble_transmon
+    if name.startswith('transmon_exact_h'):    # exact-discretisation model mode (expm + Frechet derivative per stage)
+        return systems.config_transmon_exact(horizon=int(name.split('_h')[-1]), n_steps=20), systems.ensemble_transmon
     if name == 'qubit':
         return systems.config_qubit(1, discretize=discretize), systems.ensemble_qubit
     if name == 'crosstalk':
@@ -54,12 +57,15 @@ def flop_model(cfg, counters, qp_count):
 
     counters [n, 4] = ADMM iterations, Riccati factorisations, polish rounds, QP solves.
     """
-    c = cfg['model'].A.shape[0]
+    exact = hasattr(cfg['model'], 'generators')
+    c = cfg['model'].dim_x if exact else cfg['model'].A.shape[0]
     n, m = 2 * c, cfg['dim_u']
-    p = cfg['model'].A.shape[1] // c - 1
+    p = m if exact else cfg['model'].A.shape[1] // c - 1
     H, S = cfg['clock'].horizon, cfg['clock'].n_steps
     d = cfg['experiment'].H0.shape[0]
     F_lin = H * (12 * p * c * c + 4 * p * c * m + 4 * c * m)
+    if exact:   # per stage: expm by 16 Horner + ~3 squaring matmuls (8 c^3 each), 2 x 26 Taylor terms of (1 + 2m) mat-vecs
+        F_lin = H * (19 * 8 * c ** 3 + 52 * (1 + 2 * m) * 8 * c * c)
     F_fac = H * (4 * n ** 3 + 6 * n * n * m + 2 * n * m * m + m ** 3)
     F_it = H * (4 * n * n + 8 * n * m)
     F_ls = 6 * (2 * c * (H + 1) + 2 * m * H)
@@ -117,15 +123,16 @@ def _cpu_member(job):
     plant = rs.ProcessPlant(mem.H0, mem.H1_list) if cfg.get('kind') == 'process' else \
         rs.ExpmPlant(mem.H0, mem.H1_list, lift, proj)
     stats = {}
-    A_full = cfg['model'].A
+    A_full = getattr(cfg['model'], 'A', None)
     if cfg.get('per_member_models'):
         from mpc4quantum_b200 import systems
         L, _ = systems.transmon_model_liouvillians(n_total)
         A_full = rs.taylor_discretize(list(L[k]), cfg['clock'].dt, cfg['order'])
+    exact = rs.ExactModel(list(cfg['model'].generators), cfg['clock'].dt) if cfg['name'] == 'transmon_exact' else None
     xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
                              cfg['clock'].horizon, cfg['clock'].n_steps, plant, A_full, cfg['Q'], cfg['R'],
                              cfg['Qf'], cfg['sat'], cfg['du'], warm_start=cfg['warm_start'],
-                             measure_freq=cfg['clock'].measure_freq, stats=stats)
+                             measure_freq=cfg['clock'].measure_freq, stats=stats, model=exact)
     return float(np.real(np.vdot(cfg['target'], xs[:, -1]))), int(sum(stats['qp_per_step']))
 
 
@@ -370,7 +377,7 @@ def main():
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': '%s: %s (c=%d, m=%d), horizon %d, %d MPC steps, %d perturbed plants per GPU '
                                '(seed 20220113), tight QP mode (%s)' % (args.workload, SYSTEM_NAMES.get(cfg['name'], cfg['name']),
-                                                                   cfg['model'].A.shape[0], cfg['dim_u'],
+                                                                   (cfg['model'].dim_x if hasattr(cfg['model'], 'generators') else cfg['model'].A.shape[0]), cfg['dim_u'],
                                                                    cfg['clock'].horizon, S, args.members,
                                                                    'ADMM block first' if args.admm_first else
                                                                    'warm active set first, ADMM fallback'),

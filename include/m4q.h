@@ -33,6 +33,10 @@ extern "C" {
 #define M4Q_LIFT_TRUNC32  2   /* QExperiment32: qubit block of a qutrit, trace-normalised        */
 #define M4Q_LIFT_PROCESS  3   /* QSynthesis: plant state = propagator U, model state = vec(U (x) U^*) */
 
+/* controller model (m4q_mpc_problem.model_mode) */
+#define M4Q_MODEL_TAYLOR 0    /* reference: order-k Taylor blocks [A, N_1..N_p] (vectorize.py:8-49)            */
+#define M4Q_MODEL_EXACT  1    /* extension: x+ = expm((L_0 + sum u_i L_i) dt) x, A_blocks = the m + 1 generators */
+
 /* QP solver settings (replaces the cvxpy->OSQP call at optimize.py:59) */
 typedef struct {
     double rho;          /* ADMM penalty on u = z                        (default 0.1)  */
@@ -75,6 +79,7 @@ typedef struct {
     int32_t model_per_member; /* 0: A_blocks is one model shared by all members; 1: A_blocks is [N][p+1][c][c],
                                  member k controls with its own (perturbed) model -- e.g. the output of
                                  m4q_taylor_discretize_batched regrouped per block                           */
+    int32_t model_mode;       /* M4Q_MODEL_TAYLOR (default) or M4Q_MODEL_EXACT (then p == m, measure_freq == 1) */
 } m4q_mpc_problem;
 
 int m4q_version(void);

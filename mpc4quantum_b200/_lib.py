@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libm4q.so')
 
 LIFT_IDENTITY, LIFT_COUPLED, LIFT_TRUNC32, LIFT_PROCESS = 0, 1, 2, 3
+MODEL_TAYLOR, MODEL_EXACT = 0, 1
 
 c_i32, c_i64, c_f64, c_vp = ct.c_int32, ct.c_int64, ct.c_double, ct.c_void_p
 
@@ -29,7 +30,7 @@ class MpcProblem(ct.Structure):
                 ('has_du', c_i32), ('n_targ', c_i32), ('dt', c_f64), ('sat', c_f64), ('du', c_f64),
                 ('exit_infidelity', c_f64), ('A_blocks', c_vp), ('powers', c_vp), ('Q', c_vp), ('Qf', c_vp),
                 ('R', c_vp), ('X_targ', c_vp), ('U_targ', c_vp), ('fid_vec', c_vp), ('qp', QPSettings),
-                ('model_per_member', c_i32)]
+                ('model_per_member', c_i32), ('model_mode', c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/m4q.h declares

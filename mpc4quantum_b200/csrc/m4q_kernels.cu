@@ -239,9 +239,50 @@ struct MpcArgs {
     double *ws;   // L2-resident workspaces, one per resident warp (ws_doubles<CF>(H) each)
     int slab_doubles, shared_doubles;
     int model_per_member;   // A_blocks is [n_members][nblk][C][C]: every member controls with its own model
+    double *ws_exact;       // EXACT: per resident warp, the stage matrices A_t = expm(G(u_t) dt)  [H][C][C] complex
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Exact-discretisation model mode: linearisation along (Xg, Ug) with the generators [L_0, L_1..L_M] in place of the
+// Taylor blocks.  Writes A_t (dense, per stage) to the warp's global array, B_t / Delta_t to the stage records, phi = 1.
+// ---------------------------------------------------------------------------------------------------------
 template <class CF>
+__device__ __noinline__ void linearize_exact(SlabRef sr, const double2 *gen, double dt, double2 *At, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M, CC = C * C;
+    using R_ = Rec<CF>;
+    static_assert(2 * exact_scratch<CF>() <= (CF::KP + CF::NP) * CF::LDG, "exact-stage scratch must fit the [G|W] buffers");
+    const Slab<CF> s = slab_view<CF>(sr);
+    const double *Xg = ws_Xg<CF>(sr);
+    double2 *scr = reinterpret_cast<double2 *>(s.AB);
+    double2 *xs = reinterpret_cast<double2 *>(s.va);
+#pragma unroll 1
+    for (int t = 0; t < sr.H; ++t) {
+        if (lane < C) xs[lane] = make_double2(Xg[t * N + lane], Xg[t * N + C + lane]);
+        if (lane == 0) s.phi[t] = 1.0;
+        __syncwarp();
+        exact_stage<CF>(gen, s.Ug + t * M, xs, dt, scr, lane);
+        const double2 *T = scr + CC, *b = scr + exact_b_offset<CF>();
+#pragma unroll 1
+        for (int e = lane; e < CC; e += 32) At[(size_t)t * CC + e] = T[e];
+        if (lane < N) {
+            const int r = lane < C ? lane : lane - C;
+            double *rec = ws_rec<CF>(sr, t);
+            double d = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double2 bv = b[i * C + r];
+                const double bb = lane < C ? bv.x : bv.y;
+                rec[R_::B + R_::pair(i, lane)] = bb;
+                d = fma(-bb, s.Ug[t * M + i], d);
+            }
+            rec[R_::D + lane] = d;
+        }
+        __syncwarp();
+    }
+}
+
+
+template <class CF, bool EXACT>
 __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     constexpr int C = CF::C, N = CF::N, M = CF::M;
     extern __shared__ double2 smem2[];
@@ -394,8 +435,21 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                 int n_iter = 0;
                 bool done = false;
                 while (!done && n_iter < a.max_iter) {
-                    linearize<CF, true>(sr, model, pow, lane);                  // mpc.py:175
-                    const int status = qp_solve<CF, true>(sr, model, qp, a.set, lane, cnt);   // mpc.py:189
+                    int status;
+                    if constexpr (EXACT) {
+                        double2 *At = reinterpret_cast<double2 *>(a.ws_exact) +
+                                      (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * H * C * C;
+                        linearize_exact<CF>(sr, model.blocks, a.dt, At, lane);
+                        StageOps dense;
+                        dense.blocks = At;
+                        dense.nblk = 1;
+                        dense.stage_stride = C * C;
+                        dense.soff = 0;
+                        status = qp_solve<CF, false>(sr, dense, qp, a.set, lane, cnt);
+                    } else {
+                        linearize<CF, true>(sr, model, pow, lane);                  // mpc.py:175
+                        status = qp_solve<CF, true>(sr, model, qp, a.set, lane, cnt);   // mpc.py:189
+                    }
                     if (status != 0) {
                         exit_code = status;
                         break;
@@ -1385,7 +1439,9 @@ template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long 
     if (!Slab<CF>::scratch_fits(p->p + 1, cmax(dd, CF::C))) return fail("model / plant too large for the slab scratch");
     const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2) +
                      (p->model_per_member ? 2 * (p->p + 1) * CF::C * CF::C : 0);
-    return plan(mpc_kernel<CF>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
+    if (p->model_mode == M4Q_MODEL_EXACT)
+        return plan(mpc_kernel<CF, true>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
+    return plan(mpc_kernel<CF, false>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
 }
 
 template <class CF>
@@ -1426,7 +1482,13 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
         }
         cudaGetLastError();
     }
-    mpc_kernel<CF><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
+    if (p->model_mode == M4Q_MODEL_EXACT) {
+        a.ws_exact = a.ws + (size_t)g.ctas * g.warps * ws_doubles<CF>(p->horizon);
+        mpc_kernel<CF, true><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
+    } else {
+        a.ws_exact = nullptr;
+        mpc_kernel<CF, false><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
+    }
     M4Q_CUDA(cudaGetLastError());
     if (window) {   // do not leave the window on the caller's stream
         cudaStreamAttrValue attr;
@@ -1466,6 +1528,11 @@ static int check_problem(const m4q_mpc_problem *p) {
     if (p->lift_mode == M4Q_LIFT_COUPLED && !((p->d == 4 && p->c == 8) || (p->d == 9 && p->c == 18)))
         return fail("coupled lift needs d = dA^2 and c = 2 dA^2");
     if (p->lift_mode == M4Q_LIFT_TRUNC32 && !(p->d == 3 && p->c == 4)) return fail("trunc32 lift needs d = 3, c = 4");
+    if (p->model_mode != M4Q_MODEL_TAYLOR && p->model_mode != M4Q_MODEL_EXACT) return fail("unknown model_mode");
+    if (p->model_mode == M4Q_MODEL_EXACT && p->p != p->m)
+        return fail("exact model mode: A_blocks holds the m + 1 generators, p must equal m");
+    if (p->model_mode == M4Q_MODEL_EXACT && p->measure_freq != 1)
+        return fail("exact model mode: model steps between measurements are not built, measure_freq must be 1");
     if (p->lift_mode == M4Q_LIFT_PROCESS && !(p->d == 2 && p->c == 16)) return fail("process lift needs d = 2, c = d^4 = 16");
     if (p->lift_mode == M4Q_LIFT_PROCESS && p->measure_freq != 1)
         return fail("process lift: the propagator cannot be recovered from a model step, measure_freq must be 1");
@@ -1709,6 +1776,7 @@ int64_t m4q_mpc_table_bytes(const m4q_mpc_problem *p) {
     M4Q_DISPATCH(p->c, p->m, {
         if (mpc_geometry<CF>(p, 1LL << 40, have_device, &g) != 0) return -1;
         ws = (long long)g.ctas * g.warps * ws_doubles<CF>(p->horizon);
+        if (p->model_mode == M4Q_MODEL_EXACT) ws += (long long)g.ctas * g.warps * 2 * p->horizon * CF::C * CF::C;
     });
     return (int64_t)sizeof(double) * (rup(TableLayout(2 * p->c, p->m, p->n_targ).total, 2) + ws);
 }

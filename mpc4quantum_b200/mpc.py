@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from .linearize import WrapModel, create_library, krtimes, model_blocks, size_of_library, create_power_list
-from .model import DMDcEnsemble
+from .model import DMDcEnsemble, ExactModel
 
 
 class StepClock:
@@ -154,9 +154,19 @@ class ClosedLoopPlan:
             raise TypeError('sat is mandatory: the reference fails at optimize.py:43 without it')
         lib = _lib.lib()
         _lib.require_cuda()
-        A_x, A_u = model.get_discrete()
-        wrapped = WrapModel(A_x, A_u, dim_u, order)           # validates the library size (linearize.py:23-24)
-        self.c, self.m, self.p = wrapped.dim_x, dim_u, wrapped.polyu_dim
+        self.exact = isinstance(model, ExactModel)
+        if self.exact:                                        # exact-discretisation mode: generators, no monomial library
+            if model.dim_u != dim_u:
+                raise ValueError('ExactModel has %d controls, dim_u = %d' % (model.dim_u, dim_u))
+            if abs(model.dt - clock.dt) > 1e-15 * abs(clock.dt):
+                raise ValueError('ExactModel.dt = %g differs from clock.dt = %g' % (model.dt, clock.dt))
+            self.c, self.m, self.p = model.dim_x, dim_u, dim_u
+            powers = np.eye(dim_u, dtype=np.int32)
+        else:
+            A_x, A_u = model.get_discrete()
+            wrapped = WrapModel(A_x, A_u, dim_u, order)       # validates the library size (linearize.py:23-24)
+            self.c, self.m, self.p = wrapped.dim_x, dim_u, wrapped.polyu_dim
+            powers = wrapped.powers
         if not lib.m4q_supported(self.c, self.m):
             raise NotImplementedError('no compiled kernel for (dim_x, dim_u) = (%d, %d)' % (self.c, self.m))
         self.d = int(d)
@@ -177,7 +187,10 @@ class ClosedLoopPlan:
         Ut[:, :k] = U_targ[:, :k]
         Ut[:, k:] = U_targ[:, k - 1:k]
         per_member = isinstance(model, DMDcEnsemble)
-        if per_member:
+        if self.exact:
+            blocks = _lib.dev(model.generators, np.complex128)
+            self.n_models = 0
+        elif per_member:
             # [N, c, c (p+1)] -> [N, p+1, c, c]: block 0 = A_x, block k = N_k of every member (linearize.py:32)
             stack = _lib.dev(model.A, np.complex128)
             blocks = stack.reshape(len(model), self.c, self.p + 1, self.c).permute(0, 2, 1, 3).contiguous()
@@ -187,7 +200,7 @@ class ClosedLoopPlan:
             self.n_models = 0
         self._keep = dict(
             blocks=blocks,
-            powers=_lib.dev(wrapped.powers, np.int32),
+            powers=_lib.dev(powers, np.int32),
             Q=_lib.dev(np.asarray(Q, dtype=complex).reshape(self.c, self.c), np.complex128),
             Qf=_lib.dev(np.asarray(Qf, dtype=complex).reshape(self.c, self.c), np.complex128),
             R=_lib.dev(np.real(np.asarray(R)).reshape(self.m, self.m), np.float64),
@@ -203,7 +216,8 @@ class ClosedLoopPlan:
             int(du is not None), n_targ, float(clock.dt), float(sat), float(du) if du is not None else 0.0,
             float(exit_infidelity), kp['blocks'].data_ptr(), kp['powers'].data_ptr(), kp['Q'].data_ptr(),
             kp['Qf'].data_ptr(), kp['R'].data_ptr(), kp['Xt'].data_ptr(), kp['Ut'].data_ptr(),
-            kp['fid'].data_ptr() if kp['fid'] is not None else None, st, int(per_member))
+            kp['fid'].data_ptr() if kp['fid'] is not None else None, st, int(per_member),
+            _lib.MODEL_EXACT if self.exact else _lib.MODEL_TAYLOR)
         tb = int(lib.m4q_mpc_table_bytes(ct.byref(self.prob)))
         if tb < 0:
             _lib.check(-1)
@@ -345,10 +359,15 @@ def _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model
     views that ``fit_iteration`` never writes through: it rebinds ``model.A``), so the device blocks are NOT
     re-uploaded; the updated model acts through ``model.predict`` and is returned to the caller."""
     from scipy.interpolate import interp1d
-    c = model.get_discrete()[0].shape[1]
+    if isinstance(model, ExactModel):
+        if streaming or clock.measure_freq != 1:
+            raise NotImplementedError('ExactModel: streaming updates and model steps between measurements are not built')
+        c, wrapped = model.dim_x, None
+    else:
+        c = model.get_discrete()[0].shape[1]
+        wrapped = WrapModel(*model.get_discrete(), dim_u, order)
     plan = ClosedLoopPlan(dim_u, order, X_targ, U_targ, clock, model, Q, R, Qf, sat, du, d=0, max_iter=max_iter,
                           warm_start=warm_start, capacity=1, external_plant=True)
-    wrapped = WrapModel(*model.get_discrete(), dim_u, order)
     S, mf = clock.n_steps, clock.measure_freq
     xs = [None] * (S + 1)
     us = [None] * S

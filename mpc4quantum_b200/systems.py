@@ -248,6 +248,16 @@ def config_transmon_reduced(n_steps=20, horizon=10, discretize=None):
                  warm_start=True, target=target, nominal=plant, kind='trunc32')
 
 
+def config_transmon_exact(horizon=16, n_steps=20):
+    """Config 3 with the exact-discretisation model (``ExactModel``: x+ = expm(G(u) dt) x) in place of the Taylor
+    blocks; everything else as ``config_transmon``."""
+    from .model import ExactModel
+    cfg = config_transmon(1, horizon=horizon, n_steps=n_steps, discretize=lambda L, dt, o: np.hstack([np.eye(9)] * 3))
+    cfg['model'] = ExactModel([liouvillian(h) for h in cfg['nominal'].H_list], cfg['clock'].dt)
+    cfg['name'] = 'transmon_exact'
+    return cfg
+
+
 def config_not_gate(order=1, n_steps=50, discretize=None):
     """tests/test_mpc4quantum.py:48-97 (test_NOT_gate): synthesis of the NOT gate on a resonant qubit, observed
     through the 16-dim process vector vec(U (x) U^*); dt = 0.05, H = 15, one control, identity costs, reference control

@@ -538,3 +538,55 @@ def test_per_member_models_match_reference_runs(order):
     # and the perturbed models matter: the nominal model on the same plants gives different controls
     nominal = m4q.mpc_ensemble(args[0], *args[1:6], plants.slice(0, k), *args[7:], fid_target=cfg['target'], **kw)
     assert np.abs(nominal.us - res.us[:k]).max() > 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Exact-discretisation model mode (an extension -- the oracle is the restated loop with scipy's
+# expm / expm_frechet as the model, oracle/restate.py ExactModel)
+# ----------------------------------------------------------------------------------------------------------
+def _exact_oracle(cfg, plant):
+    from oracle import restate as rs
+    stats = {}
+    model = rs.ExactModel(list(cfg['model'].generators), cfg['clock'].dt)
+    xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
+                             cfg['clock'].horizon, cfg['clock'].n_steps, rs.ExpmPlant(plant.H0, plant.H1_list), None,
+                             cfg['Q'], cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], warm_start=cfg['warm_start'],
+                             stats=stats, model=model)
+    return xs, us, ec, np.array(stats['qp_per_step'])
+
+
+def test_exact_model_closed_loop_matches_oracle():
+    cfg = systems.config_transmon_exact(horizon=16, n_steps=12)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), model, exit_code = m4q.mpc(*args, **kw)
+    xo, uo, eo, cnt = _exact_oracle(cfg, cfg['experiment'])
+    assert exit_code == 0 == eo
+    assert np.abs(us - uo).max() < U_TOL, np.abs(us - uo).max()
+    assert np.abs(xs - xo).max() < 10 * U_TOL
+    assert abs(_fid(cfg, xs[:, -1]) - _fid(cfg, xo[:, -1])) < F_TOL
+    # ensemble: perturbed plants under the exact nominal model; members 0..2 against the oracle
+    ens, _ = systems.ensemble_transmon(65536)
+    kw.pop('progress_bar')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 40), *args[7:], fid_target=cfg['target'], **kw)
+    assert (res.exit_code == 0).all()
+    for k in range(3):
+        xo, uo, eo, cnt = _exact_oracle(cfg, ens.member(k))
+        assert np.abs(res.us[k] - uo).max() < U_TOL, (k, np.abs(res.us[k] - uo).max())
+        assert abs(res.fidelity[k] - _fid(cfg, xo[:, -1])) < F_TOL
+        assert np.array_equal(res.qp_count[k], cnt)
+    # the exact model has no discretisation error: on the NOMINAL plant its one-step prediction is the plant itself,
+    # which the order-1 Taylor model misses by O(dt^2)
+    taylor = systems.config_transmon(1, horizon=16, n_steps=12)
+    (xt, ut), _, _ = m4q.mpc(*systems.mpc_args(taylor)[0], **systems.mpc_args(taylor)[1])
+    assert np.abs(ut - us).max() > 1e-4
+
+
+def test_exact_model_argument_checks():
+    cfg = systems.config_transmon_exact(horizon=8, n_steps=3)
+    args, kw = systems.mpc_args(cfg)
+    clock = m4q.StepClock(0.5, 8, 3)
+    with pytest.raises(ValueError, match='clock.dt'):
+        m4q.mpc(*args[:5], clock, *args[6:], **kw)
+    cfg['clock'].measure_freq = 2
+    with pytest.raises(RuntimeError, match='measure_freq must be 1'):
+        m4q.mpc(*args, **kw)
