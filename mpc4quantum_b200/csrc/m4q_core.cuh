@@ -1546,10 +1546,15 @@ __device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, do
 // vectorize.py:8-49 for this model mode):  x+ = expm(G(u) dt) x,  G(u) = L_0 + sum_i u_i L_i.
 //   A = expm(G dt)                      scaling and squaring of a degree-16 Taylor polynomial, C x C complex
 //   b_i = (d/du_i expm(G(u) dt)) x      = w_i(1) of  y' = G dt y,  w_i' = G dt w_i + L_i dt y,  y(0) = x, w_i(0) = 0,
-//                                       integrated exactly by Taylor series on sub-steps of norm <= 2
+//                                       integrated exactly by Taylor series on sub-steps of norm <= 4
 // gen [M+1][C][C] (shared or global), u [M], x [C] (shared).  scr: double2 [exact_scratch<CF>()] shared.
 // On return A sits in scr[C*C .. 2*C*C) and b_i[r] in scr[exact_b_offset<CF>() + i*C + r].  All lanes must call.
 // ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int strip_len(int C) {
+    for (int sl = 1; sl <= C; ++sl)
+        if (C % sl == 0 && C * C / sl <= 32) return sl;
+    return C;
+}
 template <class CF> __host__ __device__ constexpr int exact_b_offset() { return 2 * CF::C * CF::C + 2 * (1 + CF::M) * CF::C; }
 template <class CF> __host__ __device__ constexpr int exact_scratch() { return exact_b_offset<CF>() + CF::M * CF::C; }
 
@@ -1593,7 +1598,11 @@ __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, co
         ++sq;
     }
     const double sc = ldexp(1.0, -sq);
-    // ---- T = expm(G): Horner of degree 16 on G / 2^sq, then sq squarings.  Each lane owns entries lane + 32 q.
+    // strip length: smallest divisor of C with C * C / SL <= 32 lanes
+    constexpr int SL = strip_len(C), STRIPS = C * C / SL;
+    const int sl = lane < STRIPS ? lane : STRIPS - 1;
+    const int si = sl / (C / SL), sj = (sl % (C / SL)) * SL;
+    // ---- T = expm(G): Horner of degree 16 on G / 2^sq, then sq squarings.
 #pragma unroll
     for (int q = 0; q < NE; ++q) {
         const int e = lane + 32 * q;
@@ -1605,32 +1614,39 @@ __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, co
         const bool horner = k > sq;                      // first 16 passes: T = I + (sc / kk) G T; then T = T T
         const double f = horner ? sc / (double)(k - sq) : 1.0;
         const double2 *Lm = horner ? G : T;
-        double2 v[NE];
+        // each lane owns a strip of SL consecutive entries of one row: one load of Lm[i][kk] serves SL products
+        double2 v[SL];
 #pragma unroll
-        for (int q = 0; q < NE; ++q) {
-            const int e = lane + 32 * q;
-            const int ec = e < CC ? e : CC - 1;
-            const int i = ec / C, j = ec % C;
-            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        for (int q = 0; q < SL; ++q) v[q] = make_double2(0.0, 0.0);
+        const double2 *lrow = Lm + si * C, *tcol = T + sj;
 #pragma unroll
-            for (int kk = 0; kk < C; ++kk) {
-                if (kk & 1) a1 = cfma(Lm[i * C + kk], T[kk * C + j], a1);
-                else a0 = cfma(Lm[i * C + kk], T[kk * C + j], a0);
-            }
-            v[q] = make_double2(fma(a0.x + a1.x, f, (horner && i == j) ? 1.0 : 0.0), (a0.y + a1.y) * f);
+        for (int kk = 0; kk < C; ++kk) {
+            const double2 l = lrow[kk];
+#pragma unroll
+            for (int q = 0; q < SL; ++q) v[q] = cfma(l, tcol[kk * C + q], v[q]);
         }
         __syncwarp();
+        if (lane < STRIPS) {
 #pragma unroll
-        for (int q = 0; q < NE; ++q) {
-            const int e = lane + 32 * q;
-            if (e < CC) T[e] = v[q];
+            for (int q = 0; q < SL; ++q)
+                T[si * C + sj + q] = make_double2(fma(v[q].x, f, (horner && si == sj + q) ? 1.0 : 0.0), v[q].y * f);
         }
         __syncwarp();
     }
-    // ---- b_i: Taylor series of the augmented vector system on n_sub sub-steps (||G|| / n_sub <= 2, 26 terms)
-    int n_sub = (theta < 128.0) ? (int)ceil(theta * 0.5) : 64;     // also catches a non-finite generator
+    // ---- b_i: Taylor series of the augmented vector system on n_sub sub-steps (||G|| / n_sub <= 4)
+    int n_sub = (theta < 128.0) ? (int)ceil(theta * 0.25) : 32;    // also catches a non-finite generator
     if (n_sub < 1) n_sub = 1;
     const double h = 1.0 / (double)n_sub;
+    // number of terms: (theta h)^K / K! < 1e-19 (sub-step norm <= 4: K <= 36; partial sums stay below e^4)
+    int K = 0;
+    {
+        double term = 1.0;
+        const double th = theta * h;
+        while (term > 1e-19 && K < 40) {
+            ++K;
+            term *= th / (double)K;
+        }
+    }
     // vec: two buffers [(1 + M) C]: term vectors (y-term, w_1-term, ...); lane job e -> (v = e / C, r = e % C)
     double2 acc[NV];
 #pragma unroll
@@ -1640,32 +1656,63 @@ __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, co
         if (e < (1 + M) * C) vec[e] = acc[q];
     }
     __syncwarp();
+    // small systems (one job per lane): the lane's rows of G and L_v are the same in every term -- keep them in
+    // registers, so a term costs only the loads of the term vectors
+    constexpr bool ROWS_IN_REGS = (NV == 1) && (C <= 9);
+    double2 grow_r[ROWS_IN_REGS ? C : 1], lrow_r[ROWS_IN_REGS ? C : 1];
+    if constexpr (ROWS_IN_REGS) {
+        const int ec = lane < (1 + M) * C ? lane : 0;
+        const int v = ec / C, r = ec % C;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            grow_r[j] = G[r * C + j];
+            const double2 l = gen[(v > 0 ? v : 1) * CC + r * C + j];
+            lrow_r[j] = v > 0 ? make_double2(l.x * dt, l.y * dt) : make_double2(0.0, 0.0);
+        }
+    }
 #pragma unroll 1
     for (int sub = 0; sub < n_sub; ++sub) {
         int cur = 0;
 #pragma unroll 1
-        for (int k = 1; k <= 26; ++k) {
+        for (int k = 1; k <= K; ++k) {
             const double f = h / (double)k;
             const double2 *tv = vec + cur * (1 + M) * C;
             double2 *nv = vec + (cur ^ 1) * (1 + M) * C;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const int e = lane + 32 * q;
-                if (e < (1 + M) * C) {
-                    const int v = e / C, r = e % C;
+            if constexpr (ROWS_IN_REGS) {
+                if (lane < (1 + M) * C) {
+                    const int v = lane / C;
+                    const double2 *tw = tv + v * C;
                     double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
-                    const double2 *grow = G + r * C, *tw = tv + v * C;
 #pragma unroll
-                    for (int j = 0; j < C; ++j) a0 = cfma(grow[j], tw[j], a0);
-                    if (v > 0) {
-                        const double2 *lrow = gen + v * CC + r * C;
-#pragma unroll
-                        for (int j = 0; j < C; ++j) a1 = cfma(lrow[j], tv[j], a1);
+                    for (int j = 0; j < C; ++j) {
+                        a0 = cfma(grow_r[j], tw[j], a0);
+                        a1 = cfma(lrow_r[j], tv[j], a1);
                     }
-                    const double2 t = make_double2(fma(a1.x, dt, a0.x) * f, fma(a1.y, dt, a0.y) * f);
-                    nv[e] = t;
-                    acc[q].x += t.x;
-                    acc[q].y += t.y;
+                    const double2 t = make_double2((a0.x + a1.x) * f, (a0.y + a1.y) * f);
+                    nv[lane] = t;
+                    acc[0].x += t.x;
+                    acc[0].y += t.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int e = lane + 32 * q;
+                    if (e < (1 + M) * C) {
+                        const int v = e / C, r = e % C;
+                        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+                        const double2 *grow = G + r * C, *tw = tv + v * C;
+#pragma unroll
+                        for (int j = 0; j < C; ++j) a0 = cfma(grow[j], tw[j], a0);
+                        if (v > 0) {
+                            const double2 *lrow = gen + v * CC + r * C;
+#pragma unroll
+                            for (int j = 0; j < C; ++j) a1 = cfma(lrow[j], tv[j], a1);
+                        }
+                        const double2 t = make_double2(fma(a1.x, dt, a0.x) * f, fma(a1.y, dt, a0.y) * f);
+                        nv[e] = t;
+                        acc[q].x += t.x;
+                        acc[q].y += t.y;
+                    }
                 }
             }
             __syncwarp();
