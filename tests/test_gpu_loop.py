@@ -590,3 +590,48 @@ def test_exact_model_argument_checks():
     cfg['clock'].measure_freq = 2
     with pytest.raises(RuntimeError, match='measure_freq must be 1'):
         m4q.mpc(*args, **kw)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Edge cases: empty, single and ragged ensembles (member counts that do not fill the resident warps / SMs)
+# ----------------------------------------------------------------------------------------------------------
+def test_empty_single_and_ragged_ensembles():
+    cfg = systems.config_transmon(1, horizon=8, n_steps=4)
+    ens, _ = systems.ensemble_transmon(4096)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+
+    def run(n):
+        return m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, n), *args[7:], fid_target=cfg['target'], **kw)
+
+    empty = run(0)
+    assert empty.us.shape == (0, 2, 4) and empty.xs.shape == (0, 9, 5) and empty.exit_code.shape == (0,)
+    assert empty.fidelity.shape == (0,)
+    big = run(148 * 12 + 1)                        # one member more than one full wave of resident warps
+    assert (big.exit_code == 0).all() and (big.steps_done == 4).all()
+    for n in (1, 13, 149):                         # fewer members than SMs / not a multiple of the warps per CTA
+        r = run(n)
+        assert r.us.shape == (n, 2, 4)
+        assert np.array_equal(r.us, big.us[:n]) and np.array_equal(r.xs, big.xs[:n])     # member k does not see N
+        assert np.array_equal(r.fidelity, big.fidelity[:n]) and np.array_equal(r.qp_count, big.qp_count[:n])
+
+
+def test_empty_batches_of_the_standalone_entry_points():
+    from mpc4quantum_b200.experiment import expm_segments
+    from mpc4quantum_b200 import optimize
+    d, m = 3, 2
+    out = expm_segments(np.zeros((0, d * d), complex), np.zeros((0, d, d), complex), np.zeros((0, m, d, d), complex),
+                        np.zeros((0, 4, m)), 0.25)
+    assert tuple(out.shape) == (0, 4, d * d)
+    L = np.zeros((0, 3, 9, 9), complex)
+    assert tuple(m4q.vectorize.discretize_homogeneous_batched(L, 0.25, 2).shape) == (0, 9, 9 * 6)
+    cfg = systems.config_transmon(1)
+    wm = m4q.WrapModel(*cfg['model'].get_discrete(), 2, 1)
+    A, B, D = wm._along(np.zeros((0, 9, 17), complex), np.zeros((0, 2, 16)), 16)
+    assert tuple(A.shape) == (0, 16, 9, 9) and tuple(B.shape) == (0, 16, 9, 2) and tuple(D.shape) == (0, 16, 9)
+    H, c = 16, 9
+    z = lambda *s: np.zeros(s, complex)
+    X, U, obj, status, iters = optimize.quad_program_batched(
+        z(0, c), z(0, c, H + 1), np.zeros((0, m, H)), z(0, H + 1, c, c), np.zeros((0, H, m, m)), z(0, H, c, c),
+        z(0, H, c, m), z(0, H, c), np.zeros((0, m)), 1.0, 0.5)
+    assert tuple(X.shape) == (0, c, H + 1) and tuple(U.shape) == (0, m, H) and tuple(status.shape) == (0,)
