@@ -342,8 +342,10 @@ def main():
         best = max(best, 512.0 * 8 * (iters >> 2) * 8 * ctas / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     dmma_peak = best
 
-    e2e_ms, _ = timed(e2e_pass, max(2, min(args.steps, 3)))
+    e2e_pass()                                    # untimed: first use of the pinned staging buffers / allocator blocks
+    sync_all()
     e2e_steps = max(2, min(args.steps, 3))
+    e2e_ms, e2e_per_pass = timed(e2e_pass, e2e_steps)
 
     flops, per_unit = flop_model(cfg, counters, qp_count)
     traj_total = n_total * args.steps
@@ -389,7 +391,8 @@ def main():
         'factorizations_per_qp': float(counters[:, 1].sum() / max(qp_total, 1)),
         'exit_codes': {str(k): int((exit_codes == k).sum()) for k in np.unique(exit_codes)},
         'fidelity': {'min': float(fid.min()), 'median': float(np.median(fid)), 'max': float(fid.max())},
-        'e2e': {'value': n_total * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(in_bytes),
+        'e2e': {'value': n_total * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_pass': e2e_per_pass,
+                'h2d_bytes_per_step': int(in_bytes),
                 'd2h_bytes_per_step': int(out_bytes)},
         'gpu_launches': 3 * args.steps,     # build_tables + mpc_kernel + hist_kernel per pass
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
