@@ -1180,22 +1180,71 @@ __global__ void __launch_bounds__(128) expm_step_kernel_t(long long n, int m, in
                 G[e].y *= sc;
                 T[e] = make_double2((e / D == e % D) ? 1.0 : 0.0, 0.0);
             }
-            // Horner: T = I + G/1 (I + G/2 (I + ... (I + G/16)))
-#pragma unroll 1
-            for (int kk = 16; kk >= 1; --kk) {
-                const double inv = 1.0 / (double)kk;
-                double2 V[DD];
+            if constexpr (D <= 3) {
+                // degree-17 Taylor polynomial in Paterson-Stockmeyer form: 2 products for G^2, G^3, then 5 Horner steps in
+                // G^3 with T_j = T_{j+1} G^3 + (c_{3j} I + c_{3j+1} G + c_{3j+2} G^2), c_k = 1/k!  (16 products as a Horner)
+                double2 G2[DD], G3[DD];
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
                         double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-                        for (int q = 0; q < D; ++q) acc = cfma(G[i * D + q], T[q * D + j], acc);
-                        V[i * D + j] = make_double2(fma(acc.x, inv, i == j ? 1.0 : 0.0), acc.y * inv);
+                        for (int q = 0; q < D; ++q) acc = cfma(G[i * D + q], G[q * D + j], acc);
+                        G2[i * D + j] = acc;
                     }
 #pragma unroll
-                for (int e = 0; e < DD; ++e) T[e] = V[e];
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int q = 0; q < D; ++q) acc = cfma(G2[i * D + q], G[q * D + j], acc);
+                        G3[i * D + j] = acc;
+                    }
+                double c2 = 1.0 / 355687428096000.0;   // 1/17!
+                double c1 = c2 * 17.0, c0 = c1 * 16.0;
+#pragma unroll
+                for (int e = 0; e < DD; ++e)
+                    T[e] = make_double2(fma(c2, G2[e].x, fma(c1, G[e].x, (e / D == e % D) ? c0 : 0.0)),
+                                        fma(c2, G2[e].y, c1 * G[e].y));
+#pragma unroll 1
+                for (int jb = 4; jb >= 0; --jb) {
+                    c2 = c0 * (double)(3 * jb + 3);
+                    c1 = c2 * (double)(3 * jb + 2);
+                    c0 = c1 * (double)(3 * jb + 1);
+                    double2 V[DD];
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = 0; j < D; ++j) {
+                            double2 acc = make_double2(fma(c2, G2[i * D + j].x, fma(c1, G[i * D + j].x, i == j ? c0 : 0.0)),
+                                                       fma(c2, G2[i * D + j].y, c1 * G[i * D + j].y));
+#pragma unroll
+                            for (int q = 0; q < D; ++q) acc = cfma(T[i * D + q], G3[q * D + j], acc);
+                            V[i * D + j] = acc;
+                        }
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) T[e] = V[e];
+                }
+            } else {
+                // Horner: T = I + G/1 (I + G/2 (I + ... (I + G/16)))
+#pragma unroll 1
+                for (int kk = 16; kk >= 1; --kk) {
+                    const double inv = 1.0 / (double)kk;
+                    double2 V[DD];
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = 0; j < D; ++j) {
+                            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int q = 0; q < D; ++q) acc = cfma(G[i * D + q], T[q * D + j], acc);
+                            V[i * D + j] = make_double2(fma(acc.x, inv, i == j ? 1.0 : 0.0), acc.y * inv);
+                        }
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) T[e] = V[e];
+                }
             }
 #pragma unroll 1
             for (int q2 = 0; q2 < sq; ++q2) {
