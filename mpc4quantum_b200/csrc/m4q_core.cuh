@@ -73,8 +73,13 @@ template <class CF> struct Rec {
     static constexpr int B = DV + CF::N;                         // [M][C] pairs (B[r][i], B[C + r][i])
     static constexpr int D = B + rup(CF::N * CF::M, 2);          // [N]
     static constexpr int SMALL = D + CF::N;                      // end of the part the factor reads back ([B | D])
-    static constexpr int AT = SMALL;                             // [C][C] complex: A_t = sum_k phi_k(u_t) block_k
-    static constexpr int XC = AT + 2 * CF::C * CF::C;            // [N] x_t - r_t of the last rollout (adjoint sweep)
+    static constexpr int AT = SMALL;                             // [C][CA] complex: A_t = sum_k phi_k(u_t) block_k
+    // row stride of A_t in complex elements: the rows read by different lanes of the mat-vec (16-byte loads, one row
+    // per lane) must start in different banks; with C = 8 or 16 the rows are a multiple of 128 bytes apart, an 8-way
+    // conflict (measured: +10 % / +15 % on the crosstalk / gate workloads with the odd stride; C = 4 is 2-way only and
+    // was faster unpadded)
+    static constexpr int CA = (CF::C % 8 == 0) ? CF::C + 1 : CF::C;
+    static constexpr int XC = AT + 2 * CF::C * CA;               // [N] x_t - r_t of the last rollout (adjoint sweep)
     static constexpr int SIZE = XC + CF::N;
     static_assert(B % 2 == 0 && SMALL % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
     // offset of K[a][k] / B[k][i] (k = realified state index) inside their pair blocks
@@ -364,7 +369,7 @@ template <int M> __device__ __forceinline__ void spd_inverse(double (&a)[M][M], 
 //   A^T, re row:  sum m.x xr + m.y xi      A^T, im row:  sum m.x xi - m.y xr
 // so each lane reads x through two lane-dependent base pointers and one sign: no selects in the loop.
 // ---------------------------------------------------------------------------------------------------------
-template <class CF, bool TRANS>
+template <class CF, bool TRANS, int LDA = CF::C>
 __device__ __forceinline__ double cmatvec(const double2 *At, const double *x, int lane) {
     constexpr int C = CF::C, N = CF::N;
     if (lane >= N) return 0.0;
@@ -372,11 +377,11 @@ __device__ __forceinline__ double cmatvec(const double2 *At, const double *x, in
     const int r = im ? lane - C : lane;
     const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
     const double sgn = (im != TRANS) ? 1.0 : -1.0;
-    const double2 *blk = At + (TRANS ? r : r * C);
+    const double2 *blk = At + (TRANS ? r : r * LDA);
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-        const double2 m = blk[TRANS ? j * C : j];
+        const double2 m = blk[TRANS ? j * LDA : j];
         if (j & 1) {
             p1 = fma(m.x, xp[j], p1);
             q1 = fma(m.y, xq[j], q1);
@@ -400,8 +405,9 @@ __device__ __forceinline__ double cmatvec_ext(const double2 *At, const double2 *
     const int r = ext ? lane - N : (im ? lane - C : lane);
     const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
     const double sgn = (ext || im != TRANS) ? 1.0 : -1.0;
-    const double2 *blk = ext ? Ext + r * C : At + (TRANS ? r : r * C);
-    const int stride = (!ext && TRANS) ? C : 1;
+    constexpr int CA = Rec<CF>::CA;   // At is the record's A_t block (row stride CA), Ext a pair block (row stride C)
+    const double2 *blk = ext ? Ext + r * C : At + (TRANS ? r : r * CA);
+    const int stride = (!ext && TRANS) ? CA : 1;
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
     for (int j = 0; j < C; ++j, blk += stride) {
@@ -526,7 +532,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
                     s.AB[r * LDG + C + j] = -ai[q];
                     s.AB[(C + r) * LDG + j] = ai[q];
                     s.AB[(C + r) * LDG + C + j] = ar[q];
-                    reinterpret_cast<double2 *>(rec + R_::AT)[e] = make_double2(ar[q], ai[q]);
+                    reinterpret_cast<double2 *>(rec + R_::AT)[r * R_::CA + j] = make_double2(ar[q], ai[q]);
                 }
             }
         }
@@ -843,7 +849,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
 #pragma unroll
             for (int i = 0; i < M; ++i) g[i] = act ? slot[R_::B + R_::pair(i, lane)] * v : 0.0;
             warp_sum_vec<M>(g, lane);
-            atv = cmatvec<CF, true>(At, vec, lane);
+            atv = cmatvec<CF, true, R_::CA>(At, vec, lane);
         }
 #pragma unroll
         for (int i = 0; i < M; ++i) {
@@ -907,7 +913,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
 #pragma unroll
             for (int a = 0; a < M; ++a) u[a] = act ? slot[R_::K + R_::pair(a, lane)] * x : 0.0;
             warp_sum_vec<M>(u, lane);
-            ax = cmatvec<CF, false>(At, vec, lane);
+            ax = cmatvec<CF, false, R_::CA>(At, vec, lane);
         }
 #pragma unroll
         for (int a = 0; a < M; ++a) u[a] = mk[a] ? hv[a] : hv[a] - u[a];
@@ -1001,7 +1007,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
 #pragma unroll
             for (int i = 0; i < M; ++i) s.kk[t * M + i] = g[i];
         }
-        const double atl = cmatvec<CF, true>(At, lamv, lane);
+        const double atl = cmatvec<CF, true, R_::CA>(At, lamv, lane);
         lam = atl + 2.0 * apply_Q<CF>(qp.Q + t * qp.q_stride, qp.q_diag, xdv, lane);
     }
     ring_phase_store<CF>(s, ph, lane);
