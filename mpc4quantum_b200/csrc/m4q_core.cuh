@@ -243,6 +243,7 @@ struct StageOps {
     int nblk;
     int stage_stride;        // in complex elements; 0 for the fused model
     int soff;                // FUSED: offset (doubles) of the blocks in dynamic shared memory
+    int soffT;               // FUSED, c multiple of 8: offset of the transposed copies of blocks 1..p (0: none)
 };
 // FUSED = true: model blocks and cost matrices live in dynamic shared memory at known offsets
 template <bool FUSED> __device__ __forceinline__ StageOps localize(const StageOps &o) {
@@ -1303,13 +1304,16 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
             double b[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) b[i] = 0.0;
-            const double2 *blk = model.blocks + (C + r) * C;
+            // rows of N_k: [r][j] from the blocks, or (c multiple of 8) [j][r] from the transposed copies
+            const bool tr = (C % 8 == 0) && FUSED && model.soffT != 0;
+            const double2 *blk = tr ? reinterpret_cast<const double2 *>(dyn_smem() + model.soffT) + r : model.blocks + (C + r) * C;
+            const int js = tr ? C : 1;
 #pragma unroll 1
             for (int kb = 1; kb <= p; ++kb, blk += C * C) {
                 double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
-                    const double2 m = blk[j];
+                    const double2 m = blk[j * js];
                     if (j & 1) {
                         p1 = fma(m.x, pv[j], p1);
                         q1 = fma(m.y, qv[j], q1);

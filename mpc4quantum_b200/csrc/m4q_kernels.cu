@@ -307,6 +307,17 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     for (int e = threadIdx.x; e < M * M; e += blockDim.x) Rr[e] = a.tab[L.Rr + e];
 #pragma unroll 1
     for (int e = threadIdx.x; e < (a.nblk - 1) * M; e += blockDim.x) pow[e] = a.powers[e];
+    // c = 8, 16: rows of a block are a multiple of 128 bytes apart, so the one-row-per-lane loads of linearize() would be
+    // an 8-way bank conflict; it reads transposed copies instead (consecutive lanes -> consecutive addresses)
+    const int soffT = a.shared_doubles - 2 * (a.nblk - 1) * C * C;
+    if (C % 8 == 0 && !a.model_per_member) {
+        double2 *blocksT = reinterpret_cast<double2 *>(smem + soffT);
+#pragma unroll 1
+        for (int e = threadIdx.x; e < (a.nblk - 1) * C * C; e += blockDim.x) {
+            const int kb = e / (C * C), rj = e % (C * C);
+            blocksT[kb * C * C + (rj % C) * C + rj / C] = a.A_blocks[(kb + 1) * C * C + rj];
+        }
+    }
     __syncthreads();
 
     const SlabRef sr = {a.shared_doubles + warp * a.slab_doubles, H, a.nblk, cmax(dd, C),
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     model.nblk = a.nblk;
     model.stage_stride = 0;
     model.soff = 0;
+    model.soffT = (C % 8 == 0 && !a.model_per_member) ? soffT : 0;
     if (a.model_per_member) {
         // perturbed MODELS: the member's own blocks sit behind its slab (the slab stride includes them)
         model.soff = sr.off + a.slab_doubles - 2 * a.nblk * C * C;
@@ -445,6 +457,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                         dense.nblk = 1;
                         dense.stage_stride = C * C;
                         dense.soff = 0;
+                        dense.soffT = 0;
                         status = qp_solve<CF, false>(sr, dense, qp, a.set, lane, cnt);
                     } else {
                         linearize<CF, true>(sr, model, pow, lane);                  // mpc.py:175
@@ -723,6 +736,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         ops.nblk = 1;
         ops.stage_stride = C * C;
         ops.soff = 0;
+        ops.soffT = 0;
         QPData qp;
         qp.Q = wQ;
         qp.q_stride = N * N;
@@ -1480,7 +1494,9 @@ static QPSet qp_settings(const m4q_qp_settings *s) {
 }
 
 template <class CF> static int mpc_shared_doubles(int nblk) {
-    return 2 * nblk * CF::C * CF::C + 2 * CF::N * CF::N + rup(CF::M * CF::M, 2) + rup(cdiv(nblk * CF::M, 2) + 1, 2);
+    // model blocks | Q | Qf | R | monomial exponents | (c multiple of 8) transposed copies of N_1..N_p for linearize()
+    return 2 * nblk * CF::C * CF::C + 2 * CF::N * CF::N + rup(CF::M * CF::M, 2) + rup(cdiv(nblk * CF::M, 2) + 1, 2) +
+           (CF::C % 8 == 0 ? 2 * (nblk - 1) * CF::C * CF::C : 0);
 }
 
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
