@@ -9,7 +9,8 @@
 //                                                     on the fp64 tensor cores, KKT certificate)
 //   line search    mpc4quantum/mpc.py:101-125       (time-major metric paired with state-major vectors)
 //   plant          mpc4quantum/experiment.py:202-212 + mpc.py:256-260 (expm conjugation per segment)
-//   lift / proj    mpc4quantum/experiment.py:29-37, 225-235, 248-306
+//   lift / proj    mpc4quantum/experiment.py:29-37, 225-235, 248-306 (and 357-388 for gate synthesis, in m4q_kernels.cu)
+//   exact_stage    extension: expm of the generator + Frechet derivative applied to x_t, per stage
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -56,8 +57,8 @@ template <int C_, int M_> struct Cfg {
 // ---------------------------------------------------------------------------------------------------------
 // Memory plan of one member (= one warp).
 //   * shared-memory slab: the Riccati scratch (P, [A|B], W), a 2-slot ring of stage records, the control
-//     trajectories and a few vectors -- 13 KB for the transmon, (almost) independent of the horizon, so that
-//     ~16 members are resident per SM;
+//     trajectories and a few vectors -- 17.4 KB for the transmon, (almost) independent of the horizon: 12 members
+//     are resident per SM;
 //   * L2-resident workspace in global memory (one per resident warp, re-used member after member): the
 //     horizon-length data.  Per stage one RECORD [K_t | S_t^-1 | dv_t | B_t | D_t | A_t | x_t - r_t], then the trajectories
 //     Xg, Xo [(H+1) N].  Records are written with plain stores where they are produced (factor: K, S^-1, dv;
