@@ -659,3 +659,45 @@ def test_empty_batches_of_the_standalone_entry_points():
         z(0, c), z(0, c, H + 1), np.zeros((0, m, H)), z(0, H + 1, c, c), np.zeros((0, H, m, m)), z(0, H, c, c),
         z(0, H, c, m), z(0, H, c), np.zeros((0, m)), 1.0, 0.5)
     assert tuple(X.shape) == (0, c, H + 1) and tuple(U.shape) == (0, m, H) and tuple(status.shape) == (0,)
+
+
+@pytest.mark.parametrize('name', ['transmon', 'crosstalk'])
+def test_full_size_properties_65536_members(name):
+    """BASELINE configs 3 and 4 at full size (65,536 plants): invariants that need no oracle, evaluated on the device."""
+    import torch
+    from mpc4quantum_b200.ensemble import fidelity_histogram
+    n = 65536
+    if name == 'transmon':
+        cfg, (ens, _) = systems.config_transmon(1), systems.ensemble_transmon(n)
+    else:
+        cfg, (ens, _) = systems.config_crosstalk(0.0), systems.ensemble_crosstalk(n)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens, *args[7:], fid_target=cfg['target'], as_numpy=False, **kw)
+    S, d = cfg['clock'].n_steps, ens.d
+    assert int((res.exit_code != 0).sum()) == 0 and int((res.steps_done != S).sum()) == 0
+    assert float(res.us.abs().max()) <= cfg['sat'] + 1e-12                                   # optimize.py:43
+    assert float((res.us[:, :, 2:] - res.us[:, :, 1:-1]).abs().max()) <= cfg['du'] + 1e-9    # optimize.py:30
+    rho = res.xs.permute(0, 2, 1).reshape(n, S + 1, d, d)
+    tr = torch.einsum('nsii->ns', rho)
+    assert float((tr - 1).abs().max()) < 1e-10                                               # unitary plant
+    assert float((rho - rho.conj().transpose(2, 3)).abs().max()) < 1e-10
+    # purity is conserved by the plant; between measurements (measure_freq = 2 for crosstalk) xs holds the MODEL's
+    # prediction through lift / proj (mpc.py:264-267), which is not unitary
+    mf = cfg['clock'].measure_freq
+    purity = torch.einsum('nsij,nsji->ns', rho[:, ::mf], rho[:, ::mf]).real
+    assert float((purity - purity[:, :1]).abs().max()) < 1e-9
+    # step 0 does not see the plant: identical controls and SQP counts for every member
+    assert float((res.us[:, :, 0] - res.us[0, :, 0]).abs().max()) == 0.0
+    assert int((res.qp_count[:, 0] != res.qp_count[0, 0]).sum()) == 0
+    assert int((res.counters[:, 3] != res.qp_count.sum(dim=1)).sum()) == 0
+    # the fidelity histogram (config 5's reduction) counts every member once and matches numpy's
+    hist = fidelity_histogram(res.fidelity, 0.0, 1.0, 256).cpu().numpy()
+    ref, _ = np.histogram(np.clip(res.fidelity.cpu().numpy(), 0.0, 1.0), bins=256, range=(0.0, 1.0))
+    assert hist.sum() == n and np.abs(hist - ref).sum() <= 2        # a value on a bin edge may round either way
+    # members do not see each other: the same plants in reverse order give the reversed results, bit for bit
+    us_fwd, fid_fwd = res.us[:2048].clone(), res.fidelity[:2048].clone()
+    rev = m4q.EnsembleQExperiment(np.ascontiguousarray(ens.H0[:2048][::-1]), np.ascontiguousarray(ens.H1[:2048][::-1]),
+                                  ens.kind)
+    res2 = m4q.mpc_ensemble(args[0], *args[1:6], rev, *args[7:], fid_target=cfg['target'], as_numpy=False, **kw)
+    assert torch.equal(res2.us.flip(0), us_fwd) and torch.equal(res2.fidelity.flip(0), fid_fwd)
