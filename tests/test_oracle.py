@@ -160,3 +160,35 @@ def test_process_maps_and_gate_loop_vs_reference():
     p = gl['xs'][:, -1]
     pf = cfg['X_targ'][:, 0]
     assert abs(np.vdot(p - pf, p - pf).real - 8 * (1 - np.real(np.vdot(cfg['target'], p)))) < 1e-12
+
+
+def test_exact_model_oracle_against_finite_differences(unit_golden):
+    """The oracle of the exact-discretisation mode (an extension: no reference vectors exist) is pinned to first
+    principles: A_t is the propagator of the step map, B_t its derivative w.r.t. the control (central difference),
+    Delta_t closes the affine expansion, and for small dt the map tends to the reference's Taylor model."""
+    from scipy.linalg import expm
+    L = list(unit_golden['disc_transmon_L'])
+    dt = float(unit_golden['disc_transmon_dt'])
+    model = rs.ExactModel(L, dt)
+    rng = np.random.default_rng(4)
+    c, m, H = 9, 2, 5
+    X = rng.normal(size=(c, H + 1)) + 1j * rng.normal(size=(c, H + 1))
+    U = rng.uniform(-1.5, 1.5, size=(m, H))
+    A_ls, B_ls, D_ls = model.along(X, U, H)
+    for t in range(H):
+        G = (L[0] + U[0, t] * L[1] + U[1, t] * L[2]) * dt
+        assert np.abs(A_ls[t] - expm(G)).max() < 1e-14
+        assert np.abs(model.step(X[:, t], U[:, t]) - A_ls[t] @ X[:, t]).max() < 1e-13
+        for i in range(m):
+            e = np.zeros(m)
+            e[i] = 1e-6
+            fd = (model.step(X[:, t], U[:, t] + e) - model.step(X[:, t], U[:, t] - e)) / 2e-6
+            assert np.abs(B_ls[t][:, i] - fd).max() < 1e-8
+        # affine expansion around (x_t, u_t): f(x_t, u_t) = A_t x_t + B_t u_t + Delta_t
+        assert np.abs(A_ls[t] @ X[:, t] + B_ls[t] @ U[:, t] + D_ls[t] - model.step(X[:, t], U[:, t])).max() < 1e-13
+    # consistency with the reference's discretisation: the order-k Taylor blocks are the expansion of the same map
+    for order, tol in ((1, 0.3), (2, 0.05), (3, 0.01)):
+        bm = rs.BilinearModel(unit_golden['disc_transmon_o%d' % order], m, order)
+        u = 0.3 * U[:, 0]
+        err = np.abs(bm.step(X[:, 0], u) - model.step(X[:, 0], u)).max() / np.abs(X[:, 0]).max()
+        assert err < tol, (order, err)
