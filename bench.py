@@ -64,9 +64,9 @@ def flop_model(cfg, counters, qp_count):
     H, S = cfg['clock'].horizon, cfg['clock'].n_steps
     d = cfg['experiment'].H0.shape[0]
     F_lin = H * (12 * p * c * c + 4 * p * c * m + 4 * c * m)
-    if exact:   # per stage: expm by 7 Paterson-Stockmeyer + ~3 squaring products (8 c^3 each), ~22 Taylor terms of (1 + 2m)
-        #           complex mat-vecs for the Frechet vectors (term count depends on the generator norm; 22 at ||G dt|| ~ 1.5)
-        F_lin = H * (10 * 8 * c ** 3 + 22 * (1 + 2 * m) * 8 * c * c)
+    if exact:   # per stage: expm by 16 Horner + ~3 squaring products (8 c^3 each), ~22 Taylor terms of (1 + 2m) complex
+        #           mat-vecs for the Frechet vectors (term count depends on the generator norm; 22 at ||G dt|| ~ 1.5)
+        F_lin = H * (19 * 8 * c ** 3 + 22 * (1 + 2 * m) * 8 * c * c)
     F_fac = H * (4 * n ** 3 + 6 * n * n * m + 2 * n * m * m + m ** 3)
     F_it = H * (4 * n * n + 8 * n * m)
     F_ls = 6 * (2 * c * (H + 1) + 2 * m * H)

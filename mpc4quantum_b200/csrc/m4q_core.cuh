@@ -1555,7 +1555,7 @@ __device__ __noinline__ void conjugate(double2 *rho, const double2 *U, int d, do
 // ---------------------------------------------------------------------------------------------------------
 // Exact discretisation of the bilinear generator (replaces the Taylor blocks of
 // vectorize.py:8-49 for this model mode):  x+ = expm(G(u) dt) x,  G(u) = L_0 + sum_i u_i L_i.
-//   A = expm(G dt)                      scaling and squaring of a degree-17 Taylor polynomial (Paterson-Stockmeyer)
+//   A = expm(G dt)                      scaling and squaring of a degree-16 Taylor polynomial (Horner), C x C complex
 //   b_i = (d/du_i expm(G(u) dt)) x      = w_i(1) of  y' = G dt y,  w_i' = G dt w_i + L_i dt y,  y(0) = x, w_i(0) = 0,
 //                                       integrated exactly by Taylor series on sub-steps of norm <= 4
 // gen [M+1][C][C] (shared or global), u [M], x [C] (shared).  scr: double2 [exact_scratch<CF>()] shared.
@@ -1567,14 +1567,13 @@ __host__ __device__ constexpr int strip_len(int C) {
     return C;
 }
 template <class CF> __host__ __device__ constexpr int exact_b_offset() { return 2 * CF::C * CF::C + 2 * (1 + CF::M) * CF::C; }
-template <class CF> __host__ __device__ constexpr int exact_scratch() { return exact_b_offset<CF>() + CF::M * CF::C + 2 * CF::C * CF::C; }
+template <class CF> __host__ __device__ constexpr int exact_scratch() { return exact_b_offset<CF>() + CF::M * CF::C; }
 
 template <class CF>
 __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, const double2 *x, double dt, double2 *scr,
                                          int lane) {
     constexpr int C = CF::C, M = CF::M, CC = C * C, NE = cdiv(CC, 32), NV = cdiv((1 + M) * C, 32);
     double2 *G = scr, *T = scr + CC, *vec = scr + 2 * CC, *bout = scr + exact_b_offset<CF>();
-    double2 *G2 = bout + M * C, *G3 = G2 + CC;
     // ---- G = dt (L_0 + sum u_i L_i), 1-norm
     double uu[M];
 #pragma unroll
@@ -1614,35 +1613,26 @@ __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, co
     constexpr int SL = strip_len(C), STRIPS = C * C / SL;
     const int sl = lane < STRIPS ? lane : STRIPS - 1;
     const int si = sl / (C / SL), sj = (sl % (C / SL)) * SL;
-    // ---- T = expm(G): degree-17 Taylor polynomial of Gs = G / 2^sq in Paterson-Stockmeyer form,
-    //   p(Gs) = sum_{j=0..5} (Gs^3)^j (c_{3j} I + c_{3j+1} Gs + c_{3j+2} Gs^2),  c_k = 1 / k!,
-    // i.e. 2 products for G^2, G^3 and 5 Horner steps in G^3 (a plain Horner needs 16), then sq squarings.  The powers are
-    // kept unscaled, the scale goes into the coefficients: ck = sc^k / k!.  Passes, in order: 0: G2 = G G, 1: G3 = G2 G,
-    // 2..6: T = T G3 + B_j (j = 4..0), 7..: T = T T.
-    double ck = 1.0;   // sc^17 / 17!
-#pragma unroll 1
-    for (int k = 1; k <= 17; ++k) ck *= sc / (double)k;
-    const double inv_sc = ldexp(1.0, sq);
-    if (lane < STRIPS) {   // T = B_5 = c15 I + c16 G + c17 G2 needs G2: start from c15 I + c16 G, G2 added after pass 0
+    // (A Paterson-Stockmeyer evaluation -- 7 + sq products instead of 16 + sq, +13 % throughput of this mode -- agreed with
+    // scipy to 1.4e-15 instead of 8e-16; the closed loop of this mode amplifies such differences by up to 1e12 on badly
+    // mismatched plants, and the Horner form tracked the CPU oracle 100x closer there, so it stays.)
+    // ---- T = expm(G): Horner of degree 16 on G / 2^sq, then sq squarings.
 #pragma unroll
-        for (int q = 0; q < SL; ++q) {
-            const int e = si * C + sj + q;
-            const double c16 = ck * 17.0 * inv_sc, c15 = c16 * 16.0 * inv_sc;
-            const double2 g = G[e];
-            T[e] = make_double2(fma(c16, g.x, si == sj + q ? c15 : 0.0), c16 * g.y);
-        }
+    for (int q = 0; q < NE; ++q) {
+        const int e = lane + 32 * q;
+        if (e < CC) T[e] = make_double2(e / C == e % C ? 1.0 : 0.0, 0.0);
     }
     __syncwarp();
-    double c_hi = ck * 17.0 * inv_sc * 16.0 * inv_sc * 15.0 * inv_sc;   // c14, the top coefficient of block j = 4
 #pragma unroll 1
-    for (int pass = 0; pass < 7 + sq; ++pass) {
-        const double2 *Am = pass == 0 ? G : (pass == 1 ? G2 : T);
-        const double2 *Bm = pass <= 1 ? G : (pass <= 6 ? G3 : T);
-        // each lane owns a strip of SL consecutive entries of one row: one load of Am[i][kk] serves SL products
+    for (int k = 16 + sq; k >= 1; --k) {
+        const bool horner = k > sq;                      // first 16 passes: T = I + (sc / kk) G T; then T = T T
+        const double f = horner ? sc / (double)(k - sq) : 1.0;
+        const double2 *Lm = horner ? G : T;
+        // each lane owns a strip of SL consecutive entries of one row: one load of Lm[i][kk] serves SL products
         double2 v[SL];
 #pragma unroll
         for (int q = 0; q < SL; ++q) v[q] = make_double2(0.0, 0.0);
-        const double2 *lrow = Am + si * C, *tcol = Bm + sj;
+        const double2 *lrow = Lm + si * C, *tcol = T + sj;
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
             const double2 l = lrow[kk];
@@ -1651,31 +1641,10 @@ __device__ __noinline__ void exact_stage(const double2 *gen, const double *u, co
         }
         __syncwarp();
         if (lane < STRIPS) {
-            if (pass >= 2 && pass <= 6) {   // + B_j = c_{3j} I + c_{3j+1} G + c_{3j+2} G2, j = 6 - pass
-                const double c2 = c_hi, c1 = c2 * (double)(3 * (6 - pass) + 2) * inv_sc;
-                const double c0 = c1 * (double)(3 * (6 - pass) + 1) * inv_sc;
 #pragma unroll
-                for (int q = 0; q < SL; ++q) {
-                    const int e = si * C + sj + q;
-                    const double2 g = G[e], g2 = G2[e];
-                    T[e] = make_double2(v[q].x + fma(c2, g2.x, fma(c1, g.x, si == sj + q ? c0 : 0.0)),
-                                        v[q].y + fma(c2, g2.y, c1 * g.y));
-                }
-            } else {
-                double2 *dst = pass == 0 ? G2 : (pass == 1 ? G3 : T);
-#pragma unroll
-                for (int q = 0; q < SL; ++q) {
-                    const int e = si * C + sj + q;
-                    dst[e] = v[q];
-                    if (pass == 0) {   // complete B_5 now that G2 exists
-                        T[e].x = fma(ck, v[q].x, T[e].x);
-                        T[e].y = fma(ck, v[q].y, T[e].y);
-                    }
-                }
-            }
+            for (int q = 0; q < SL; ++q)
+                T[si * C + sj + q] = make_double2(fma(v[q].x, f, (horner && si == sj + q) ? 1.0 : 0.0), v[q].y * f);
         }
-        if (pass >= 2 && pass <= 6) c_hi = c_hi * (double)(3 * (6 - pass) + 2) * inv_sc * (double)(3 * (6 - pass) + 1) * inv_sc *
-                                           (double)(3 * (6 - pass)) * inv_sc;
         __syncwarp();
     }
     // ---- b_i: Taylor series of the augmented vector system on n_sub sub-steps (||G|| / n_sub <= 4)
