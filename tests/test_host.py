@@ -217,3 +217,31 @@ def test_qsynthesis_lift_proj_match_the_reference():
     p = g['lift2'][0]
     assert m4q.QProcess.lift(p) is p and m4q.QProcess.proj(p) is p
     assert m4q.QProcess.lift_mode == 3 and m4q.split_blocks(np.arange(16).reshape(4, 4), 2, 2).shape == (4, 2, 2)
+
+
+def test_model_containers_for_ensembles_and_exact_mode():
+    """Host-side containers added for the ensemble entry point: DMDcEnsemble (perturbed models) and ExactModel."""
+    L, params = systems.transmon_model_liouvillians(6)
+    assert L.shape == (6, 3, 9, 9) and set(params) == {'model_anharm_scale', 'model_amplitude_scale'}
+    for k in range(6):        # batched Liouvillians == the single-model helper (vectorize.py:52-75 in the |a><b| basis)
+        a = systems.destroy(3)
+        H0 = params['model_anharm_scale'][k] * (-2 * np.pi * 0.1 / 0.25) * systems.proj(3, 2)
+        HX = params['model_amplitude_scale'][k] * 0.5 * (a.conj().T + a)
+        assert np.abs(L[k, 0] - vectorize.liouvillian(H0)).max() < 1e-15
+        assert np.abs(L[k, 1] - vectorize.liouvillian(HX)).max() < 1e-15
+    A = np.stack([rs.taylor_discretize(list(L[k]), 0.25, 1) for k in range(6)])
+    ens = m4q.DMDcEnsemble(9, 9, 18, A)
+    assert len(ens) == 6 and len(ens.slice(2, 5)) == 3
+    Ax, Au = ens.member(4).get_discrete()
+    assert Ax.shape == (9, 9) and Au.shape == (9, 18) and np.array_equal(np.hstack([Ax, Au]), A[4])
+    assert np.array_equal(ens.get_discrete()[0], A[0][:, :9])
+    ex = m4q.ExactModel(list(L[0]), 0.25)
+    assert (ex.dim_x, ex.dim_u, ex.dt) == (9, 2, 0.25) and ex.generators.shape == (3, 9, 9)
+    cfg = systems.config_transmon_exact(horizon=4, n_steps=2)
+    assert isinstance(cfg['model'], m4q.ExactModel) and cfg['model'].dim_u == cfg['dim_u']
+    gate = systems.config_not_gate(1, discretize=rs.taylor_discretize)
+    assert gate['x0'].shape == (16,) and gate['model'].A.shape == (16, 32) and gate['experiment'].lift_mode == 3
+    # ||p - pf||^2 = 8 (1 - F): the reference test's callback and the device threshold are the same statement
+    p = gate['x0']
+    pf = gate['X_targ'][:, 0]
+    assert abs(np.vdot(p - pf, p - pf).real - 8 * (1 - np.real(np.vdot(gate['target'], p)))) < 1e-12
