@@ -47,6 +47,9 @@ typedef struct {
     int32_t max_polish;  /* active-set rounds per polish                 (default 8)    */
     int32_t admm_first;  /* tight mode only. 0: warm-started active-set rounds first, ADMM block as fallback (default);
                             1: always run an ADMM block to eps before the active-set rounds */
+    int32_t adaptive_rho;/* 0 / 1: rho is rescaled from the primal / dual residual ratio at a few check points, with a
+                            re-factorisation, as OSQP's adaptive_rho does (default); -1: fixed rho */
+    int32_t reserved_;   /* keeps the struct a multiple of 8 bytes; must be 0 */
 } m4q_qp_settings;
 
 /* Problem description of the closed loop (mpc.py:128-304).  Shared (member-independent) data. */
@@ -80,6 +83,25 @@ typedef struct {
                                  member k controls with its own (perturbed) model -- e.g. the output of
                                  m4q_taylor_discretize_batched regrouped per block                           */
     int32_t model_mode;       /* M4Q_MODEL_TAYLOR (default) or M4Q_MODEL_EXACT (then p == m, measure_freq == 1) */
+    /* measurement noise of QExperiment.set_sigma (experiment.py:193-194, :212): every measured plant state gets
+       sigma * (N(0,1) + i N(0,1)) added per component, and -- as in the reference, which restarts the next simulate()
+       from the stored measurement (mpc.py:259) -- the plant continues from the noisy state.  Counter-based generator
+       (Philox4x32-10) keyed by (noise_seed, member), counter (step, component): results do not depend on the launch
+       geometry.  noise_sigma = 0 switches it off. */
+    double noise_sigma;
+    uint64_t noise_seed;
+    /* streaming model update (mpc.py:281-285 with OnlineDMDc.fit_iteration, model.py:295-313), per member, after every
+       MPC step: z = [x; phi(u) (x) x], gamma = 1 / (1 + z^T P z), A += gamma (y - A z)(P z)^T, P = (P - gamma P z (P z)^T)
+       / discount.  As in the reference the controller keeps linearising the operators captured before the loop; the
+       updated A is used by the model steps between measurements (measure_freq > 1) and returned.
+       streaming = 0: off.  stream_A [N][c][c (p+1)] complex (in: initial model of every member, out: final),
+       stream_P [N][c (p+1)][c (p+1)] complex (in: initial P, out: final). */
+    int32_t streaming;
+    int32_t fidelity_sqrt;    /* 0: fidelity = Re<fid_vec, x> (= <psi|rho|psi> for a pure target); 1: its square root,
+                                 qutip.fidelity's convention (tests/test_mpc4quantum.py:590, :691) */
+    double stream_discount;   /* OnlineDMDc.discount (model.py:28), 1 = none */
+    double *stream_A;
+    double *stream_P;
 } m4q_mpc_problem;
 
 int m4q_version(void);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libm4q.so')
+LIB_PATH = os.environ.get('M4Q_LIB') or os.path.join(_HERE, 'libm4q.so')     # M4Q_LIB: measurement aid (build variants)
 
 LIFT_IDENTITY, LIFT_COUPLED, LIFT_TRUNC32, LIFT_PROCESS = 0, 1, 2, 3
 MODEL_TAYLOR, MODEL_EXACT = 0, 1
@@ -20,7 +20,7 @@ c_i32, c_i64, c_f64, c_vp = ct.c_int32, ct.c_int64, ct.c_double, ct.c_void_p
 class QPSettings(ct.Structure):
     """m4q_qp_settings (include/m4q.h)."""
     _fields_ = [('rho', c_f64), ('alpha', c_f64), ('eps', c_f64), ('max_admm', c_i32), ('polish', c_i32),
-                ('max_polish', c_i32), ('admm_first', c_i32)]
+                ('max_polish', c_i32), ('admm_first', c_i32), ('adaptive_rho', c_i32), ('reserved_', c_i32)]
 
 
 class MpcProblem(ct.Structure):
@@ -30,7 +30,9 @@ class MpcProblem(ct.Structure):
                 ('has_du', c_i32), ('n_targ', c_i32), ('dt', c_f64), ('sat', c_f64), ('du', c_f64),
                 ('exit_infidelity', c_f64), ('A_blocks', c_vp), ('powers', c_vp), ('Q', c_vp), ('Qf', c_vp),
                 ('R', c_vp), ('X_targ', c_vp), ('U_targ', c_vp), ('fid_vec', c_vp), ('qp', QPSettings),
-                ('model_per_member', c_i32), ('model_mode', c_i32)]
+                ('model_per_member', c_i32), ('model_mode', c_i32), ('noise_sigma', c_f64), ('noise_seed', ct.c_uint64),
+                ('streaming', c_i32), ('fidelity_sqrt', c_i32), ('stream_discount', c_f64), ('stream_A', c_vp),
+                ('stream_P', c_vp)]
 
 
 # name -> (restype, argtypes); every symbol include/m4q.h declares
@@ -135,6 +137,6 @@ def stream_ptr(stream=None):
     return c_vp(st.cuda_stream)
 
 
-def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0, admm_first=0):
+def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0, admm_first=0, adaptive_rho=0):
     """Zeros select the library defaults (include/m4q.h)."""
-    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, admm_first)
+    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, admm_first, adaptive_rho, 0)

@@ -38,7 +38,10 @@ __host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r
 __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };   // 128 registers
-template <> struct Tiles<9, 2> { static constexpr int MAXW = 12; };   // 3 warps per scheduler: 168 registers, no spills
+#ifndef M4Q_MAXW_92
+#define M4Q_MAXW_92 12
+#endif
+template <> struct Tiles<9, 2> { static constexpr int MAXW = M4Q_MAXW_92; };   // 12: 3 warps per scheduler, 168 registers, no spills
 template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };   // 15 fit; measured faster than 12 x 168 registers
 template <> struct Tiles<16, 3> { static constexpr int MAXW = 8; };
 template <> struct Tiles<16, 1> { static constexpr int MAXW = 8; };
@@ -52,6 +55,15 @@ template <int C_, int M_> struct Cfg {
     static constexpr int LDG = cmin(next_mod(QP, 4, 16), next_mod(QP, 12, 16));
     static_assert(LDP >= Q && LDP % 2 == 0, "T11 and the control columns are staged in the P buffer");
     static_assert(QP > Q, "one padding column of G carries the affine term");
+    // Second-generation factor (riccati_factor2, N <= 24): W^T = G^T P stays in the DMMA accumulators and feeds the
+    // second product T = W^T G straight from registers.  That works without a single shuffle because the contraction
+    // index of a k-step is free to be permuted: step (kt, e) contracts over k = 8 kt + 2 c4 + e, which is exactly the
+    // column the accumulator fragment of lane (g8, c4) holds.  Operand rows are then 2 LD apart between neighbouring
+    // c4, so conflict-free fragment loads want LD = 2 or 6 (mod 8).
+    static constexpr int NT = cdiv(N, 8), GT = cdiv(Q + 1, 8), TT = cdiv(Q, 8), KR = 8 * NT;
+    static constexpr bool FAC2 = NT <= 3;
+    static constexpr int LDP2 = cmin(next_mod(KR, 2, 8), next_mod(KR, 6, 8));
+    static constexpr int LDG2 = cmin(next_mod(8 * GT, 2, 8), next_mod(8 * GT, 6, 8));
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -86,7 +98,8 @@ template <class CF> struct Rec {
     // offset of K[a][k] / B[k][i] (k = realified state index) inside their pair blocks
     __host__ __device__ static constexpr int pair(int ctl, int k) { return (ctl * CF::C + (k % CF::C)) * 2 + (k >= CF::C); }
     // during the vector sweeps whole records are staged in the [G | W] buffers (only live inside the factor)
-    static_assert(2 * SIZE <= (CF::KP + CF::NP) * CF::LDG, "record ring does not fit the factor scratch");
+    static_assert(CF::FAC2 ? 2 * SIZE <= CF::KR * (CF::LDP2 + CF::LDG2) : 2 * SIZE <= (CF::KP + CF::NP) * CF::LDG,
+                  "record ring does not fit the factor scratch");
 };
 template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
     return H * Rec<CF>::SIZE + 2 * (H + 1) * CF::N;
@@ -94,6 +107,8 @@ template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
 
 template <class CF> struct Slab {
     double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr, *mbar;
+    double *recring;   // 2-slot ring of whole stage records for the vector sweeps (aliases the factor scratch)
+    double *xd;        // 2 N doubles of scratch for the general-cost adjoint sweep
     int *mask;
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
@@ -102,7 +117,7 @@ template <class CF> struct Slab {
     // scratch of the linearisation (2 x [p][M] derivative weights) and of the plant step (4 complex d x d):
     // aliases W, which is only live inside the Riccati factor
     __host__ __device__ static bool scratch_fits(int nblk, int dd) {
-        return cmax(8 * dd, 2 * CF::M * nblk) <= CF::NP * CF::LDG;
+        return cmax(8 * dd, 2 * CF::M * nblk) <= (CF::FAC2 ? CF::KR * CF::LDG2 : CF::NP * CF::LDG);
     }
     // dd = plant state length in complex numbers (d*d)
     __host__ __device__ static int layout(Slab *s, double *base, int H, int nblk, int dd) {
@@ -114,10 +129,20 @@ template <class CF> struct Slab {
         };
         Slab dummy;
         Slab *q = s ? s : &dummy;
-        take(&q->P, CF::NP * CF::LDP);    // P_{t+1}, zero padded
-        take(&q->AB, CF::KP * CF::LDG);   // G = [A_t | B~_t], zero padded
-        take(&q->W, CF::NP * CF::LDG);    // W = P G
-        q->scr = q->W;
+        if (CF::FAC2) {
+            take(&q->P, CF::KR * CF::LDP2);   // P_{t+1}, zero padded, [8 NT][LDP2]
+            take(&q->AB, CF::KR * CF::LDG2);  // G = [A_t | B~_t | D~_t], zero padded, [8 NT][LDG2]
+            take(&q->W, M * N);               // K_t for the update of P (W = P G itself never leaves the registers)
+            q->scr = q->AB;
+            q->recring = q->P;
+        } else {
+            take(&q->P, CF::NP * CF::LDP);    // P_{t+1}, zero padded
+            take(&q->AB, CF::KP * CF::LDG);   // G = [A_t | B~_t], zero padded
+            take(&q->W, CF::NP * CF::LDG);    // W = P G
+            q->scr = q->W;
+            q->recring = q->AB;
+        }
+        take(&q->xd, 2 * N);
         take(&q->T21, M * N);
         take(&q->S, M * M);
         take(&q->ring, 2 * (Rec<CF>::SMALL - Rec<CF>::B));   // factor: [B_t | D_t] of two stages
@@ -281,7 +306,7 @@ template <bool FUSED> __device__ __forceinline__ QPData localize(const QPData &q
 
 struct QPSet {
     double rho, alpha, eps;
-    int max_admm, polish, max_polish, admm_first;
+    int max_admm, polish, max_polish, admm_first, adaptive_rho;
 };
 
 struct Counters {
@@ -716,9 +741,285 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Second-generation Riccati matrix sweep (CF::FAC2).  Same mathematics and the same outputs as riccati_factor;
+// what changes is the traffic through shared memory, the resource this kernel is bound by:
+//   * W^T = G^T P (G = [A_t | B~_t | D~_t], N x (Q + 1)) is accumulated in DMMA fragments and consumed by the second
+//     product T = W^T G straight from the registers: a k-step (kt, e) contracts over k = 8 kt + 2 c4 + e, the very
+//     column of W^T that lane (g8, c4) holds in accumulator element e, so the A operand of the second product IS
+//     the accumulator -- no store, no reload, no shuffle (the permutation of the contraction index is harmless as
+//     long as both operands use it);
+//   * the G fragments are the A operand of the first product and the B operand of the second;
+//   * dv_t = P_{t+1} D~_t is row Q of W^T and goes from the accumulators to the stage record;
+//   * P_t = Qbar_t + T11 - T21^T K is applied to the accumulator fragments of T11; each lane stores its part of the
+//     upper block triangle and its mirror image, so P stays exactly symmetric.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF, bool FUSED>
+__device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, double rho_half,
+                                             bool masked, int lane) {
+    constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q;
+    constexpr int NT = CF::NT, GT = CF::GT, TT = CF::TT, KR = CF::KR, LDP = CF::LDP2, LDG = CF::LDG2;
+    using R_ = Rec<CF>;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
+    const int g8 = lane >> 2, c4 = lane & 3;   // fragment coordinates of this lane
+    // P <- Qf with zero padding; G zeroed once (padding rows / columns are never written afterwards)
+#pragma unroll 1
+    for (int e = lane; e < KR * LDP; e += 32) {
+        const int i = e / LDP, j = e % LDP;
+        s.P[e] = (i < N && j < N) ? qp.Qf[i * N + j] : 0.0;
+    }
+#pragma unroll 1
+    for (int e = lane; e < KR * LDG; e += 32) s.AB[e] = 0.0;
+    constexpr int BD = R_::SMALL - R_::B;   // [B_t | D_t]
+    prefetch_block<BD>(s.ring + ((H - 1) & 1) * BD, ws_rec<CF>(sr, H - 1) + R_::B, lane);
+#pragma unroll 1
+    for (int t = H - 1; t >= 0; --t) {
+        const double *phi_t = s.phi + t * ops.nblk;
+        const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
+        const double *Bt = s.ring + (t & 1) * BD, *Dt = Bt + (R_::D - R_::B);
+        double *rec = ws_rec<CF>(sr, t);
+        cp_async_wait_all();
+        __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
+        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * BD, ws_rec<CF>(sr, t - 1) + R_::B, lane);
+        // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
+        {
+            constexpr int NE = cdiv(C * C, 32);
+            double ar[NE], ai[NE];
+#pragma unroll
+            for (int q = 0; q < NE; ++q) ar[q] = ai[q] = 0.0;
+            const double2 *bp = blk0 + lane;
+            const int qlast = (C * C - 1 - lane) >> 5;   // last valid q of this lane (loads clamped, not predicated)
+#pragma unroll 1
+            for (int kb = 0; kb < ops.nblk; ++kb, bp += C * C) {
+                const double ph = phi_t[kb];
+                double2 v[NE];
+#pragma unroll
+                for (int q = 0; q < NE; ++q) v[q] = bp[32 * (q < qlast ? q : qlast)];
+#pragma unroll
+                for (int q = 0; q < NE; ++q) {
+                    ar[q] = fma(ph, v[q].x, ar[q]);
+                    ai[q] = fma(ph, v[q].y, ai[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NE; ++q) {
+                const int e = lane + 32 * q;
+                if (e < C * C) {
+                    const int r = e / C, j = e % C;
+                    s.AB[r * LDG + j] = ar[q];
+                    s.AB[r * LDG + C + j] = -ai[q];
+                    s.AB[(C + r) * LDG + j] = ai[q];
+                    s.AB[(C + r) * LDG + C + j] = ar[q];
+                    reinterpret_cast<double2 *>(rec + R_::AT)[r * R_::CA + j] = make_double2(ar[q], ai[q]);
+                }
+            }
+        }
+        // B~ into G[:, N:Q], D~ into G[:, Q]
+#pragma unroll 1
+        for (int e = lane; e < N * M; e += 32) {
+            const int k = e / M, i = e % M;
+            const bool fixed = masked && s.mask[t * M + i] != 0;
+            s.AB[k * LDG + N + i] = fixed ? 0.0 : Bt[R_::pair(i, k)];
+        }
+        if (lane < N) {
+            double dt = Dt[lane];
+            if (masked) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    const int mk = s.mask[t * M + i];
+                    if (mk) dt = fma(Bt[R_::pair(i, lane)], mk == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
+                }
+            }
+            s.AB[lane * LDG + Q] = dt;
+        }
+        __syncwarp();
+        // ---- W^T = G^T P: tile (qi, mi) holds W^T[qi*8 + g8][mi*8 + 2*c4 + {0,1}]
+        double w[GT][NT][2];
+#pragma unroll
+        for (int qi = 0; qi < GT; ++qi)
+#pragma unroll
+            for (int mi = 0; mi < NT; ++mi) w[qi][mi][0] = w[qi][mi][1] = 0.0;
+        {
+            // operand rows of k-step (kt, e): 8 kt + 2 c4 + e
+            const double *gp = s.AB + (2 * c4) * LDG + g8, *pp = s.P + (2 * c4) * LDP + g8;
+            double gf[GT], pf[NT];
+#pragma unroll
+            for (int qi = 0; qi < GT; ++qi) gf[qi] = gp[qi * 8];
+#pragma unroll
+            for (int mi = 0; mi < NT; ++mi) pf[mi] = pp[mi * 8];
+#pragma unroll 1
+            for (int ks = 0; ks < 2 * NT; ++ks) {
+                // next step's fragments in flight while this step's MMAs issue; the last step reloads its own
+                const int last = ks + 1 == 2 * NT;
+                const int adv = last ? 0 : ((ks & 1) ? 7 : 1);   // rows: e = 0 -> e = 1 (+1), e = 1 -> next tile (+7)
+                gp += adv * LDG;
+                pp += adv * LDP;
+                double gn[GT], pn[NT];
+#pragma unroll
+                for (int qi = 0; qi < GT; ++qi) gn[qi] = gp[qi * 8];
+#pragma unroll
+                for (int mi = 0; mi < NT; ++mi) pn[mi] = pp[mi * 8];
+#pragma unroll
+                for (int qi = 0; qi < GT; ++qi)
+#pragma unroll
+                    for (int mi = 0; mi < NT; ++mi) dmma(w[qi][mi], gf[qi], pf[mi]);
+#pragma unroll
+                for (int qi = 0; qi < GT; ++qi) gf[qi] = gn[qi];
+#pragma unroll
+                for (int mi = 0; mi < NT; ++mi) pf[mi] = pn[mi];
+            }
+        }
+        // dv_t = P_{t+1} D~_t = row Q of W^T: held by the lanes with g8 == Q % 8, columns mi*8 + 2 c4 + {0, 1}
+        if (g8 == Q % 8) {
+#pragma unroll
+            for (int mi = 0; mi < NT; ++mi) {
+                const int j = mi * 8 + 2 * c4;
+                if (j < N) *reinterpret_cast<double2 *>(rec + R_::DV + j) = make_double2(w[Q / 8][mi][0], w[Q / 8][mi][1]);
+            }
+        }
+        // ---- T = W^T G, upper block triangle of the leading Q x Q part: A operand = the accumulators of W^T
+        double tt[TT][TT][2];
+#pragma unroll
+        for (int qi = 0; qi < TT; ++qi)
+#pragma unroll
+            for (int ni = qi; ni < TT; ++ni) tt[qi][ni][0] = tt[qi][ni][1] = 0.0;
+        {
+            const double *gp = s.AB + (2 * c4) * LDG + g8;
+#pragma unroll
+            for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double gb[TT];
+#pragma unroll
+                    for (int ni = 0; ni < TT; ++ni) gb[ni] = gp[(kt * 8 + e) * LDG + ni * 8];
+#pragma unroll
+                    for (int qi = 0; qi < TT; ++qi)
+#pragma unroll
+                        for (int ni = qi; ni < TT; ++ni) dmma(tt[qi][ni], w[qi][kt][e], gb[ni]);
+                }
+        }
+        // ---- publish the control columns: T12[i][a] (i < N) -> T21[a][i], T22 -> S (upper part, mirrored)
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int ja = N + a, na = ja / 8, ca = (ja % 8) / 2, ea = ja % 2;
+            if (c4 == ca) {
+#pragma unroll
+                for (int qi = 0; qi < TT; ++qi) {
+                    if (qi > na) continue;
+                    const int i = qi * 8 + g8;
+                    const double v = tt[qi][na][ea];
+                    if (i < N) s.T21[a * N + i] = v;
+                    else if (i <= ja) {
+                        s.S[(i - N) * M + a] = v;
+                        s.S[a * M + (i - N)] = v;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // S = R~ + rho/2 + B~^T P B~ ; invert (every lane redundantly, M <= 3)
+        double Sm[M][M], Si[M][M];
+        const double *Rt = qp.R + t * qp.r_stride;
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            const bool fa = masked && s.mask[t * M + a] != 0;
+#pragma unroll
+            for (int b = 0; b < M; ++b) {
+                const bool fb = masked && s.mask[t * M + b] != 0;
+                double v = s.S[a * M + b];
+                if (fa || fb) v = (a == b) ? 1.0 : 0.0;
+                else v += Rt[a * M + b] + (a == b ? rho_half : 0.0);
+                Sm[a][b] = v;
+            }
+        }
+        spd_inverse<M>(Sm, Si);
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < M; ++a)
+#pragma unroll
+                for (int b = 0; b < M; ++b) rec[R_::SINV + a * M + b] = Si[a][b];
+        }
+        if (lane < N) {
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+                double kv = 0.0;
+#pragma unroll
+                for (int b = 0; b < M; ++b) kv = fma(Si[a][b], s.T21[b * N + lane], kv);
+                rec[R_::K + R_::pair(a, lane)] = kv;
+                s.W[a * N + lane] = kv;
+            }
+        }
+        __syncwarp();
+        // ---- P_t = Qbar_t + T11 - T21^T K on the accumulator fragments; upper block triangle + mirror image
+        const double *Qt = qp.Q + t * qp.q_stride;
+#pragma unroll
+        for (int qi = 0; qi < NT; ++qi) {
+            const int i = qi * 8 + g8;
+            const int ic = i < N ? i : N - 1;
+            double t21[M];
+#pragma unroll
+            for (int a = 0; a < M; ++a) t21[a] = s.T21[a * N + ic];
+#pragma unroll
+            for (int ni = qi; ni < NT; ++ni) {
+                const int j0 = ni * 8 + 2 * c4;
+                const int jc = j0 < N ? j0 : N - 2;     // N is even: the pair (j0, j0 + 1) is inside or outside together
+                double v0 = tt[qi][ni][0], v1 = tt[qi][ni][1];
+#pragma unroll
+                for (int a = 0; a < M; ++a) {
+                    const double2 kp = *reinterpret_cast<const double2 *>(s.W + a * N + jc);
+                    v0 = fma(-t21[a], kp.x, v0);
+                    v1 = fma(-t21[a], kp.y, v1);
+                }
+                const bool in = i < N && j0 < N;
+                if (qp.q_diag) {
+                    if (ni == qi) {
+                        const double qd = Qt[ic * N + ic];
+                        v0 += (i == j0) ? qd : 0.0;
+                        v1 += (i == j0 + 1) ? qd : 0.0;
+                    }
+                } else {
+                    v0 += Qt[ic * N + jc];
+                    v1 += Qt[ic * N + jc + 1];
+                }
+                if (ni > qi) {
+                    // off-diagonal tile: whole pair + its transpose (padding stays zero)
+                    if (in) {
+                        *reinterpret_cast<double2 *>(s.P + i * LDP + j0) = make_double2(v0, v1);
+                        s.P[j0 * LDP + i] = v0;
+                        s.P[(j0 + 1) * LDP + i] = v1;
+                    }
+                } else {
+                    // diagonal tile: the elements on or above the diagonal, each with its mirror image
+                    if (in && i <= j0) {
+                        s.P[i * LDP + j0] = v0;
+                        s.P[j0 * LDP + i] = v0;
+                    }
+                    if (in && i <= j0 + 1) {
+                        s.P[i * LDP + j0 + 1] = v1;
+                        s.P[(j0 + 1) * LDP + i] = v1;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <class CF, bool FUSED>
+__device__ __forceinline__ void factor_dispatch(const SlabRef &sr, const StageOps &ops, const QPData &qp, double rho_half,
+                                                bool masked, int lane) {
+    if constexpr (CF::FAC2) riccati_factor2<CF, FUSED>(sr, ops, qp, rho_half, masked, lane);
+    else riccati_factor<CF, FUSED>(sr, ops, qp, rho_half, masked, lane);
+}
+
 // stage record t of the workspace -> slot (t & 1) of the record ring in the [G | W] buffers
 template <class CF> __device__ __forceinline__ double *rec_slot(const Slab<CF> &s, int t) {
-    return s.AB + (t & 1) * Rec<CF>::SIZE;
+    return s.recring + (t & 1) * Rec<CF>::SIZE;
 }
 template <class CF>
 __device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int lane) {
@@ -878,6 +1179,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     }
     // forward: record 0 is still in slot 0
     double x = (act && !refine) ? s.x0[lane] : 0.0;
+    double dumax = 0.0;   // REFINE: largest correction of a control (its convergence measure)
     if (WRITE_X && act && !refine) Xo[lane] = x;
     double r_n = (WRITE_X && act && !refine) ? qp.r[lane] : 0.0;   // target of the stage, register-prefetched
 #pragma unroll 1
@@ -924,6 +1226,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
 #pragma unroll
             for (int a = 1; a < M; ++a) uv = (lane == a) ? u[a] : uv;
             s.Uo[t * M + lane] = refine ? s.Uo[t * M + lane] + uv : uv;
+            if (refine) dumax = fmax(dumax, fabs(uv));
         }
         if (act) {
             double xn = ax + dq;
@@ -938,7 +1241,9 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     ring_phase_store<CF>(s, ph, lane);
     __syncwarp();
     // a non-finite state anywhere in the rollout propagates to x_H
-    return __any_sync(FULL, !isfinite(x)) ? 1.0 : 0.0;
+    const bool bad = __any_sync(FULL, !isfinite(x));
+    if (refine) return bad ? -1.0 : warp_max(dumax);   // size of the correction (negative: non-finite)
+    return bad ? 1.0 : 0.0;
 }
 
 // (Qbar v)[lane] for v in shared memory
@@ -974,9 +1279,9 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
     unsigned ph = ring_phase_load<CF>(s);
     prefetch_stage<CF>(s, sr, H - 1, lane);
     double xd_n = act ? Xo[(H - 1) * N + lane] - qp.r[(H - 1) * N + lane] : 0.0;
-    if (act) s.P[lane] = Xo[H * N + lane] - qp.r[H * N + lane];   // P is dead outside the factor
+    if (act) s.xd[lane] = Xo[H * N + lane] - qp.r[H * N + lane];
     __syncwarp();
-    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.P, lane);
+    double lam = 2.0 * apply_Q<CF>(qp.Qf, qp.q_diag, s.xd, lane);
     double gmax = 0.0;
     __syncwarp();
 #pragma unroll 1
@@ -985,7 +1290,7 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
         const double2 *At = reinterpret_cast<const double2 *>(rec_slot<CF>(s, t) + R_::AT);
         const double *Rt = qp.R + t * qp.r_stride;
         double *lamv = (t & 1) ? s.vb : s.va;
-        double *xdv = s.P + (t & 1) * N;
+        double *xdv = s.xd + (t & 1) * N;
         const double xd = xd_n;
         if (act) {
             lamv[lane] = lam;
@@ -1058,24 +1363,63 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
 #pragma unroll 1
             for (int e = lane; e < HM; e += 32) s.mask[e] = 0;   // the sweeps read the working set: none in ADMM
             __syncwarp();
-            riccati_factor<CF, FUSED>(sr, ops_in, qp_in, rho_half, false, lane);
+            // rho is adapted like OSQP does (optimize.py:59 -> OSQP's adaptive_rho): at a few check points the penalty
+            // is rescaled by sqrt(normalised primal residual / normalised dual residual) when that ratio is far from
+            // one, the scaled dual y follows, and the Riccati factorisation is redone with the new rho.
+            double rho = set.rho, rh = rho_half;
+            factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, rh, false, lane);
             cnt.factor++;
+            int next_check = 5;
             for (int it = 0; it < set.max_admm; ++it) {
-                riccati_solve<CF, FUSED>(sr, qp_in, rho_half, SWEEP_ADMM, !set.polish, lane);
+                riccati_solve<CF, FUSED>(sr, qp_in, rh, SWEEP_ADMM, !set.polish, lane);
                 cnt.admm++;
                 bool bad = false;
+                double rp = 0.0, rd = 0.0, nu = 0.0, ny = 0.0;
 #pragma unroll 1
                 for (int e = lane; e < HM; e += 32) {
                     const int t = e / M, i = e % M;
                     const double u = s.Uo[e], zo = s.z[e];
                     const double uh = set.alpha * u + (1.0 - set.alpha) * zo;
                     const double zn = fmin(fmax(uh + s.y[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
-                    s.y[e] += uh - zn;
+                    const double yn = s.y[e] + uh - zn;
+                    s.y[e] = yn;
                     s.z[e] = zn;
-                    bad |= !(fabs(u - zn) < eps) || !(set.rho * fabs(zn - zo) < eps);
+                    bad |= !(fabs(u - zn) < eps) || !(rho * fabs(zn - zo) < eps);
+                    rp = fmax(rp, fabs(u - zn));
+                    rd = fmax(rd, fabs(zn - zo));
+                    nu = fmax(nu, fmax(fabs(u), fabs(zn)));
+                    ny = fmax(ny, fabs(yn));
                 }
                 __syncwarp();
                 if (!__any_sync(FULL, bad)) break;   // warp vote: every lane's slice of the residuals is below eps
+                if (set.adaptive_rho && it + 1 == next_check && it + 1 < set.max_admm) {
+                    next_check = 2 * next_check + 5;
+                    rp = warp_max(rp);
+                    rd = warp_max(rd);
+                    nu = warp_max(nu);
+                    ny = warp_max(ny);
+                    // both residuals relative to the size of what they are residuals of (u = z; the dual rho y)
+                    const double pr = rp / fmax(nu, 1e-12), dr = rd / fmax(ny, 1e-12);
+                    double ratio = sqrt(fmax(pr, 1e-12) / fmax(dr, 1e-12));
+                    ratio = fmin(fmax(ratio, 0.05), 20.0);
+                    const double rho_new = fmin(fmax(rho * ratio, 1e-6), 1e6);
+                    if (rho_new > 5.0 * rho || rho_new < 0.2 * rho) {
+                        const double sc = rho / rho_new;
+#pragma unroll 1
+                        for (int e = lane; e < HM; e += 32) s.y[e] *= sc;
+                        __syncwarp();
+                        rho = rho_new;
+                        rh = 0.5 * rho;
+                        factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, rh, false, lane);
+                        cnt.factor++;
+                    }
+                }
+            }
+            if (rho != set.rho) {   // hand y over in the units of the configured rho (warm start of the next solve)
+                const double sc = rho / set.rho;
+#pragma unroll 1
+                for (int e = lane; e < HM; e += 32) s.y[e] *= sc;
+                __syncwarp();
             }
         }
         if (!set.polish) {
@@ -1117,17 +1461,19 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         __syncwarp();
         bool certified = false;
         for (int round = 0; round < set.max_polish; ++round) {
-            riccati_factor<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
+            factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
             cnt.factor++;
             cnt.polish++;
             x_nonfinite = riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_POLISH, true, lane) != 0.0;
             double gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
                                     : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             bool stable = false;
+            double du_last = -1.0;   // size of the last refinement correction (< 0: none yet)
 #pragma unroll 1
             for (int rf = 0;; ++rf) {
                 const double gs = fmax(1.0, gmax);
-                bool changed = false, visible = false, unstationary = false;
+                bool changed = false, visible = false, unstationary = false, rough = false;
+                double umax = 0.0;
 #pragma unroll 1
                 for (int e = lane; e < HM; e += 32) {
                     const int t = e / M, i = e % M;
@@ -1135,13 +1481,15 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                     const double u = s.Uo[e], g = s.kk[e];
                     const double lo = box_lo(s, qp.sat, t, i), hi = box_hi(s, qp.sat, t, i);
                     int nm = mk;
+                    umax = fmax(umax, fabs(u));
                     if (mk == 0) {
                         if (u < lo - 1e-12) nm = 1;
                         else if (u > hi + 1e-12) nm = 2;
                         // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
-                        // cost-to-go has outgrown fp64 (long horizons with the order-1 model)
+                        // cost-to-go is badly scaled (long horizons with the order-1 model)
                         visible |= !(fabs(g) <= 1e-9 * gs);
                         unstationary |= !(fabs(g) <= 1e-8 * gs);
+                        rough |= !(fabs(g) <= 1e-5 * gs);
                     } else if (mk == 1) {
                         if (g < -1e-10 * gs) nm = 0;
                     } else {
@@ -1154,19 +1502,34 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 }
                 __syncwarp();
                 if (__any_sync(FULL, changed)) break;   // the working set moved: next round
-                // same working set again: certified if the free controls are stationary; a visible gradient means
-                // the Riccati solve lost accuracy (ill-conditioned cost-to-go) -- iterative refinement with the same
-                // factorisation, at most three times, then the ADMM fallback (and, in the end, exit code 2)
-                if (!__any_sync(FULL, visible) || (rf == 3 && !__any_sync(FULL, unstationary))) {
-                    stable = true;
-                    certified = !__any_sync(FULL, unstationary);
+                // Same working set again: certified if the free controls are stationary.  A visible gradient means the
+                // Riccati solve lost accuracy (ill-conditioned cost-to-go): iterative refinement with the same
+                // factorisation (feedback form: the correction is rolled out through A - B K, so it does not
+                // re-amplify).  The adjoint gradient itself is evaluated through the unstable open-loop dynamics and
+                // has a noise floor of ~ eps * ||prod A_t||^2; once the refinement has CONVERGED (its correction is
+                // below 1e-9 of the control scale) what is left of the gradient is that evaluation noise, and the point
+                // is the optimum of the working set to the accuracy fp64 offers -- accepted if the residual gradient is
+                // small (1e-5 relative), which a wrong factorisation would not produce.
+                const bool vis = __any_sync(FULL, visible), unst = __any_sync(FULL, unstationary);
+                if (!vis) {
+                    stable = certified = true;
                     break;
                 }
-                if (rf == 3) {
+                if (du_last >= 0.0 && du_last <= 1e-9 * fmax(1.0, warp_max(umax)) && !__any_sync(FULL, rough)) {
+                    stable = certified = true;
+                    break;
+                }
+                if (rf == 6) {
+                    stable = true;
+                    certified = !unst;
+                    break;
+                }
+                du_last = riccati_solve<CF, FUSED, true>(sr, qp_in, 0.0, SWEEP_REFINE, true, lane);
+                x_nonfinite = du_last < 0.0;
+                if (x_nonfinite) {
                     stable = true;
                     break;
                 }
-                x_nonfinite = riccati_solve<CF, FUSED, true>(sr, qp_in, 0.0, SWEEP_REFINE, true, lane) != 0.0;
                 cnt.admm += 2;   // one correction sweep + one adjoint sweep
                 gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
                                  : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);

@@ -250,10 +250,11 @@ template <class CF>
 __device__ __noinline__ void linearize_exact(SlabRef sr, const double2 *gen, double dt, double2 *At, int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M, CC = C * C;
     using R_ = Rec<CF>;
-    static_assert(2 * exact_scratch<CF>() <= (CF::KP + CF::NP) * CF::LDG, "exact-stage scratch must fit the [G|W] buffers");
+    static_assert(2 * exact_scratch<CF>() <= (CF::FAC2 ? CF::KR * (CF::LDP2 + CF::LDG2) : (CF::KP + CF::NP) * CF::LDG),
+                  "exact-stage scratch must fit the factor scratch");
     const Slab<CF> s = slab_view<CF>(sr);
     const double *Xg = ws_Xg<CF>(sr);
-    double2 *scr = reinterpret_cast<double2 *>(s.AB);
+    double2 *scr = reinterpret_cast<double2 *>(s.recring);
     double2 *xs = reinterpret_cast<double2 *>(s.va);
 #pragma unroll 1
     for (int t = 0; t < sr.H; ++t) {
@@ -1490,6 +1491,7 @@ static QPSet qp_settings(const m4q_qp_settings *s) {
     q.max_admm = (s && s->max_admm > 0) ? s->max_admm : 400;
     q.max_polish = (s && s->max_polish > 0) ? s->max_polish : 8;
     q.admm_first = s ? s->admm_first : 0;
+    q.adaptive_rho = (s && s->adaptive_rho < 0) ? 0 : 1;
     return q;
 }
 

@@ -564,8 +564,11 @@ def mpc_loop(x0, dim_u, order, X_targ, U_targ, dt, horizon, n_steps, plant, A_fu
     xs[0] = np.asarray(x0, dtype=complex)
     qp_counts = []
     exit_code = 0
+    trace = stats.setdefault('trace', []) if (stats is not None and stats.get('want_trace')) else None
     for step in range(S):
         n_iter, done = 0, False
+        if trace is not None:       # what the controller knows when step `step` starts (teacher-forcing fixtures)
+            trace.append(dict(Xg=Xg.copy(), Ug=Ug.copy(), x=np.asarray(plant.lift(xs[step]), dtype=complex).copy()))
         while not done and n_iter < max_iter:
             A_ls, B_ls, D_ls = model.along(Xg, Ug, H)
             u_prev = us[step - 1] if step > 1 else U_ref[:, 0]
