@@ -39,7 +39,7 @@ __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };   // 128 registers
 #ifndef M4Q_MAXW_92
-#define M4Q_MAXW_92 12
+#define M4Q_MAXW_92 16
 #endif
 template <> struct Tiles<9, 2> { static constexpr int MAXW = M4Q_MAXW_92; };   // 12: 3 warps per scheduler, 168 registers, no spills
 template <> struct Tiles<8, 2> { static constexpr int MAXW = 16; };   // 15 fit; measured faster than 12 x 168 registers
@@ -60,9 +60,12 @@ template <int C_, int M_> struct Cfg {
     // index of a k-step is free to be permuted: step (kt, e) contracts over k = 8 kt + 2 c4 + e, which is exactly the
     // column the accumulator fragment of lane (g8, c4) holds.  Operand rows are then 2 LD apart between neighbouring
     // c4, so conflict-free fragment loads want LD = 2 or 6 (mod 8).
-    static constexpr int NT = cdiv(N, 8), GT = cdiv(Q + 1, 8), TT = cdiv(Q, 8), KR = 8 * NT;
+    static constexpr int NT = cdiv(N, 8), GT = cdiv(Q + 1, 8), TT = cdiv(Q, 8);
+    // operand rows: the N real ones plus, when N is not a multiple of 8, ONE row of zeros that every padding index of
+    // the last contraction tile is mapped to (instead of 8 NT - N zero rows: 2 x 130 doubles less per member for N = 18)
+    static constexpr int KR = (N % 8 == 0) ? N : N + 1;
     static constexpr bool FAC2 = NT <= 3;
-    static constexpr int LDP2 = cmin(next_mod(KR, 2, 8), next_mod(KR, 6, 8));
+    static constexpr int LDP2 = cmin(next_mod(8 * NT, 2, 8), next_mod(8 * NT, 6, 8));
     static constexpr int LDG2 = cmin(next_mod(8 * GT, 2, 8), next_mod(8 * GT, 6, 8));
 };
 
@@ -94,11 +97,13 @@ template <class CF> struct Rec {
     static constexpr int CA = (CF::C % 8 == 0) ? CF::C + 1 : CF::C;
     static constexpr int XC = AT + 2 * CF::C * CA;               // [N] x_t - r_t of the last rollout (adjoint sweep)
     static constexpr int SIZE = XC + CF::N;
+    // ring slots start on 128-byte boundaries: a 512-byte cp.async request then covers 4 shared-memory lines, not 5
+    static constexpr int SLOT = rup(SIZE, 16), BDSLOT = rup(D + CF::N - B, 16);
     static_assert(B % 2 == 0 && SMALL % 2 == 0 && SIZE % 2 == 0, "records are moved in 16-byte chunks");
     // offset of K[a][k] / B[k][i] (k = realified state index) inside their pair blocks
     __host__ __device__ static constexpr int pair(int ctl, int k) { return (ctl * CF::C + (k % CF::C)) * 2 + (k >= CF::C); }
     // during the vector sweeps whole records are staged in the [G | W] buffers (only live inside the factor)
-    static_assert(CF::FAC2 ? 2 * SIZE <= CF::KR * (CF::LDP2 + CF::LDG2) : 2 * SIZE <= (CF::KP + CF::NP) * CF::LDG,
+    static_assert(CF::FAC2 ? SLOT + SIZE <= CF::KR * (CF::LDP2 + CF::LDG2) : SLOT + SIZE <= (CF::KP + CF::NP) * CF::LDG,
                   "record ring does not fit the factor scratch");
 };
 template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
@@ -123,21 +128,22 @@ template <class CF> struct Slab {
     __host__ __device__ static int layout(Slab *s, double *base, int H, int nblk, int dd) {
         constexpr int N = CF::N, M = CF::M;
         int o = 0;
-        auto take = [&](double **dst, int cnt) {
+        auto take = [&](double **dst, int cnt, int align = 2) {
+            o = rup(o, align);
             if (s) *dst = base + o;
             o += rup(cnt, 2);
         };
         Slab dummy;
         Slab *q = s ? s : &dummy;
         if (CF::FAC2) {
-            take(&q->P, CF::KR * CF::LDP2);   // P_{t+1}, zero padded, [8 NT][LDP2]
-            take(&q->AB, CF::KR * CF::LDG2);  // G = [A_t | B~_t | D~_t], zero padded, [8 NT][LDG2]
+            take(&q->P, CF::KR * CF::LDP2, 16);   // P_{t+1}, zero padded, [KR][LDP2]
+            take(&q->AB, CF::KR * CF::LDG2);  // G = [A_t | B~_t | D~_t], zero padded, [KR][LDG2]
             take(&q->W, M * N);               // K_t for the update of P (W = P G itself never leaves the registers)
             q->scr = q->AB;
             q->recring = q->P;
         } else {
             take(&q->P, CF::NP * CF::LDP);    // P_{t+1}, zero padded
-            take(&q->AB, CF::KP * CF::LDG);   // G = [A_t | B~_t], zero padded
+            take(&q->AB, CF::KP * CF::LDG, 16);   // G = [A_t | B~_t], zero padded
             take(&q->W, CF::NP * CF::LDG);    // W = P G
             q->scr = q->W;
             q->recring = q->AB;
@@ -145,7 +151,7 @@ template <class CF> struct Slab {
         take(&q->xd, 2 * N);
         take(&q->T21, M * N);
         take(&q->S, M * M);
-        take(&q->ring, 2 * (Rec<CF>::SMALL - Rec<CF>::B));   // factor: [B_t | D_t] of two stages
+        take(&q->ring, 2 * Rec<CF>::BDSLOT, 16);   // factor: [B_t | D_t] of two stages
         take(&q->kk, H * M);
         take(&q->hl, H * M);
         take(&q->phi, H * nblk);
@@ -154,8 +160,8 @@ template <class CF> struct Slab {
         take(&q->z, H * M);
         take(&q->y, H * M);
         take(&q->x0, N);
-        take(&q->va, N);
-        take(&q->vb, N);
+        take(&q->va, N + 2);   // sweep vectors: imaginary half at offset rup(C, 2)
+        take(&q->vb, N + 2);
         take(&q->xT, N);
         take(&q->mbar, 4);   // two mbarriers (one per record-ring slot) + their phase bits
         take(&q->lo0, M);
@@ -422,30 +428,39 @@ __device__ __forceinline__ double cmatvec(const double2 *At, const double *x, in
 // The same loop with M extra rows in the lanes N .. N+M-1: row a of Ext ([M][C] pairs (e[r], e[C + r])) dotted with
 // x.  Backward sweep: Ext = B_t -> B_t^T v;  forward sweep: Ext = K_t -> K_t x.  The control-space reductions thus
 // cost no shuffle tree: lane N + a holds the result and broadcasts it.
+// x is held with its imaginary half at offset XP = rup(C, 2) (sweep_idx), so that both halves can be read as 16-byte
+// pairs: C / 2 + 1 wide loads per half instead of C narrow ones.
+template <class CF> __device__ __forceinline__ int sweep_idx(int lane) {
+    return lane + (lane >= CF::C ? rup(CF::C, 2) - CF::C : 0);
+}
 template <class CF, bool TRANS>
 __device__ __forceinline__ double cmatvec_ext(const double2 *At, const double2 *Ext, const double *x, int lane) {
-    constexpr int C = CF::C, N = CF::N, M = CF::M;
+    constexpr int C = CF::C, N = CF::N, M = CF::M, XP = rup(C, 2);
     static_assert(N + M <= 32, "no free lanes for the control rows");
     if (lane >= N + M) return 0.0;
     const bool ext = lane >= N;
     const bool im = !ext && lane >= C;
     const int r = ext ? lane - N : (im ? lane - C : lane);
-    const double *xp = x + (im ? C : 0), *xq = x + (im ? 0 : C);
+    const double *xp = x + (im ? XP : 0), *xq = x + (im ? 0 : XP);
     const double sgn = (ext || im != TRANS) ? 1.0 : -1.0;
     constexpr int CA = Rec<CF>::CA;   // At is the record's A_t block (row stride CA), Ext a pair block (row stride C)
     const double2 *blk = ext ? Ext + r * C : At + (TRANS ? r : r * CA);
     const int stride = (!ext && TRANS) ? CA : 1;
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < C; ++j, blk += stride) {
+    for (int j = 0; j + 1 < C; j += 2) {
+        const double2 ma = blk[0], mb = blk[stride];
+        blk += 2 * stride;
+        const double2 xa = *reinterpret_cast<const double2 *>(xp + j), xb = *reinterpret_cast<const double2 *>(xq + j);
+        p0 = fma(ma.x, xa.x, p0);
+        q0 = fma(ma.y, xb.x, q0);
+        p1 = fma(mb.x, xa.y, p1);
+        q1 = fma(mb.y, xb.y, q1);
+    }
+    if constexpr (C % 2 == 1) {
         const double2 m = *blk;
-        if (j & 1) {
-            p1 = fma(m.x, xp[j], p1);
-            q1 = fma(m.y, xq[j], q1);
-        } else {
-            p0 = fma(m.x, xp[j], p0);
-            q0 = fma(m.y, xq[j], q0);
-        }
+        p0 = fma(m.x, xp[C - 1], p0);
+        q0 = fma(m.y, xq[C - 1], q0);
     }
     return fma(sgn, q0 + q1, p0 + p1);
 }
@@ -519,16 +534,16 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
 #pragma unroll 1
     for (int e = lane; e < KP * LDG; e += 32) s.AB[e] = 0.0;
     constexpr int BD = R_::SMALL - R_::B;   // [B_t | D_t]
-    prefetch_block<BD>(s.ring + ((H - 1) & 1) * BD, ws_rec<CF>(sr, H - 1) + R_::B, lane);
+    prefetch_block<BD>(s.ring + ((H - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
-        const double *Bt = s.ring + (t & 1) * BD, *Dt = Bt + (R_::D - R_::B);
+        const double *Bt = s.ring + (t & 1) * R_::BDSLOT, *Dt = Bt + (R_::D - R_::B);
         double *rec = ws_rec<CF>(sr, t);
         cp_async_wait_all();
         __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
-        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * BD, ws_rec<CF>(sr, t - 1) + R_::B, lane);
+        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, t - 1) + R_::B, lane);
         // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
         {
             constexpr int NE = cdiv(C * C, 32);
@@ -774,16 +789,16 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
 #pragma unroll 1
     for (int e = lane; e < KR * LDG; e += 32) s.AB[e] = 0.0;
     constexpr int BD = R_::SMALL - R_::B;   // [B_t | D_t]
-    prefetch_block<BD>(s.ring + ((H - 1) & 1) * BD, ws_rec<CF>(sr, H - 1) + R_::B, lane);
+    prefetch_block<BD>(s.ring + ((H - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
         const double *phi_t = s.phi + t * ops.nblk;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
-        const double *Bt = s.ring + (t & 1) * BD, *Dt = Bt + (R_::D - R_::B);
+        const double *Bt = s.ring + (t & 1) * R_::BDSLOT, *Dt = Bt + (R_::D - R_::B);
         double *rec = ws_rec<CF>(sr, t);
         cp_async_wait_all();
         __syncwarp();   // B_t, D_t have landed; P_{t+1} of the previous stage is complete
-        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * BD, ws_rec<CF>(sr, t - 1) + R_::B, lane);
+        if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, t - 1) + R_::B, lane);
         // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
         {
             constexpr int NE = cdiv(C * C, 32);
@@ -817,21 +832,17 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
                 }
             }
         }
-        // B~ into G[:, N:Q], D~ into G[:, Q]
-#pragma unroll 1
-        for (int e = lane; e < N * M; e += 32) {
-            const int k = e / M, i = e % M;
-            const bool fixed = masked && s.mask[t * M + i] != 0;
-            s.AB[k * LDG + N + i] = fixed ? 0.0 : Bt[R_::pair(i, k)];
-        }
+        // B~ into G[:, N:Q], D~ into G[:, Q]: lane k < N owns row k; the working set of the stage is read once
+        int mk[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) mk[i] = masked ? s.mask[t * M + i] : 0;
         if (lane < N) {
             double dt = Dt[lane];
-            if (masked) {
 #pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const int mk = s.mask[t * M + i];
-                    if (mk) dt = fma(Bt[R_::pair(i, lane)], mk == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
-                }
+            for (int i = 0; i < M; ++i) {
+                const double b = Bt[R_::pair(i, lane)];
+                s.AB[lane * LDG + N + i] = mk[i] ? 0.0 : b;
+                if (mk[i]) dt = fma(b, mk[i] == 1 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i), dt);
             }
             s.AB[lane * LDG + Q] = dt;
         }
@@ -843,25 +854,29 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
 #pragma unroll
             for (int mi = 0; mi < NT; ++mi) w[qi][mi][0] = w[qi][mi][1] = 0.0;
         {
-            // operand rows of k-step (kt, e): 8 kt + 2 c4 + e
-            const double *gp = s.AB + (2 * c4) * LDG + g8, *pp = s.P + (2 * c4) * LDP + g8;
+            // operand rows of k-step (kt, e): 8 kt + 2 c4 + e, padding indices of the last tile -> the zero row N
+            auto row_of = [&](int ks) {
+                const int r = (ks >> 1) * 8 + 2 * c4 + (ks & 1);
+                return r < N ? r : KR - 1;
+            };
+            const double *gb0 = s.AB + g8, *pb0 = s.P + g8;
             double gf[GT], pf[NT];
+            {
+                const int r = row_of(0);
 #pragma unroll
-            for (int qi = 0; qi < GT; ++qi) gf[qi] = gp[qi * 8];
+                for (int qi = 0; qi < GT; ++qi) gf[qi] = gb0[r * LDG + qi * 8];
 #pragma unroll
-            for (int mi = 0; mi < NT; ++mi) pf[mi] = pp[mi * 8];
+                for (int mi = 0; mi < NT; ++mi) pf[mi] = pb0[r * LDP + mi * 8];
+            }
 #pragma unroll 1
             for (int ks = 0; ks < 2 * NT; ++ks) {
                 // next step's fragments in flight while this step's MMAs issue; the last step reloads its own
-                const int last = ks + 1 == 2 * NT;
-                const int adv = last ? 0 : ((ks & 1) ? 7 : 1);   // rows: e = 0 -> e = 1 (+1), e = 1 -> next tile (+7)
-                gp += adv * LDG;
-                pp += adv * LDP;
+                const int r = row_of(ks + 1 < 2 * NT ? ks + 1 : ks);
                 double gn[GT], pn[NT];
 #pragma unroll
-                for (int qi = 0; qi < GT; ++qi) gn[qi] = gp[qi * 8];
+                for (int qi = 0; qi < GT; ++qi) gn[qi] = gb0[r * LDG + qi * 8];
 #pragma unroll
-                for (int mi = 0; mi < NT; ++mi) pn[mi] = pp[mi * 8];
+                for (int mi = 0; mi < NT; ++mi) pn[mi] = pb0[r * LDP + mi * 8];
 #pragma unroll
                 for (int qi = 0; qi < GT; ++qi)
 #pragma unroll
@@ -887,14 +902,16 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
 #pragma unroll
             for (int ni = qi; ni < TT; ++ni) tt[qi][ni][0] = tt[qi][ni][1] = 0.0;
         {
-            const double *gp = s.AB + (2 * c4) * LDG + g8;
+            const double *gb0 = s.AB + g8;
 #pragma unroll
             for (int kt = 0; kt < NT; ++kt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
+                    int r = kt * 8 + 2 * c4 + e;
+                    if (kt == NT - 1 && N % 8 != 0) r = r < N ? r : KR - 1;
                     double gb[TT];
 #pragma unroll
-                    for (int ni = 0; ni < TT; ++ni) gb[ni] = gp[(kt * 8 + e) * LDG + ni * 8];
+                    for (int ni = 0; ni < TT; ++ni) gb[ni] = gb0[r * LDG + ni * 8];
 #pragma unroll
                     for (int qi = 0; qi < TT; ++qi)
 #pragma unroll
@@ -904,19 +921,18 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
         // ---- publish the control columns: T12[i][a] (i < N) -> T21[a][i], T22 -> S (upper part, mirrored)
 #pragma unroll
         for (int a = 0; a < M; ++a) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int ja = N + a, na = ja / 8, ca = (ja % 8) / 2, ea = ja % 2;
+            const int ja = N + a, na = ja / 8, ca = (ja % 8) / 2, ea = ja % 2;   // constants after unrolling
             if (c4 == ca) {
 #pragma unroll
                 for (int qi = 0; qi < TT; ++qi) {
-                    if (qi > na) continue;
-                    const int i = qi * 8 + g8;
-                    const double v = tt[qi][na][ea];
-                    if (i < N) s.T21[a * N + i] = v;
-                    else if (i <= ja) {
-                        s.S[(i - N) * M + a] = v;
-                        s.S[a * M + (i - N)] = v;
+                    if (qi <= na) {
+                        const int i = qi * 8 + g8;
+                        const double v = tt[qi][na][ea];
+                        if (qi * 8 + 7 < N || i < N) s.T21[a * N + i] = v;
+                        else if (i <= ja) {
+                            s.S[(i - N) * M + a] = v;
+                            s.S[a * M + (i - N)] = v;
+                        }
                     }
                 }
             }
@@ -927,10 +943,10 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
         const double *Rt = qp.R + t * qp.r_stride;
 #pragma unroll
         for (int a = 0; a < M; ++a) {
-            const bool fa = masked && s.mask[t * M + a] != 0;
+            const bool fa = mk[a] != 0;
 #pragma unroll
             for (int b = 0; b < M; ++b) {
-                const bool fb = masked && s.mask[t * M + b] != 0;
+                const bool fb = mk[b] != 0;
                 double v = s.S[a * M + b];
                 if (fa || fb) v = (a == b) ? 1.0 : 0.0;
                 else v += Rt[a * M + b] + (a == b ? rho_half : 0.0);
@@ -1019,7 +1035,7 @@ __device__ __forceinline__ void factor_dispatch(const SlabRef &sr, const StageOp
 
 // stage record t of the workspace -> slot (t & 1) of the record ring in the [G | W] buffers
 template <class CF> __device__ __forceinline__ double *rec_slot(const Slab<CF> &s, int t) {
-    return s.recring + (t & 1) * Rec<CF>::SIZE;
+    return s.recring + (t & 1) * Rec<CF>::SLOT;
 }
 template <class CF>
 __device__ __forceinline__ void prefetch_stage(const Slab<CF> &s, const SlabRef &sr, int t, int lane) {
@@ -1071,6 +1087,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
     const QPData qp = localize<FUSED>(qp_in);
     const int H = sr.H;
     const bool act = lane < N;
+    const int vix = (N + M <= 32) ? sweep_idx<CF>(lane) : lane;   // layout of the sweep vectors (cmatvec_ext)
     // the refinement variant is a separate (cold) instantiation: the hot copy stays small for the instruction cache
     const bool adj = !REFINE && mode == SWEEP_ADJOINT, refine = REFINE;
     double *Xo = ws_Xo<CF>(sr);
@@ -1125,7 +1142,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         double *vec = (t & 1) ? s.vb : s.va;
         const double v = dv_n + p;
         double ql = ql_n;
-        if (act) vec[lane] = v;
+        if (act) vec[vix] = v;
         if (t > 0 && act && !adj && !refine) {
             dv_n = ws_rec<CF>(sr, t - 1)[R_::DV + lane];
             ql_n = qp.qlin[(t - 1) * N + lane];
@@ -1188,7 +1205,7 @@ __device__ __noinline__ double riccati_solve(SlabRef sr, const QPData &qp_in, do
         const double2 *At = reinterpret_cast<const double2 *>(slot + R_::AT);
         double *vec = (t & 1) ? s.vb : s.va;
         if (act) {
-            vec[lane] = x;
+            vec[vix] = x;
             if (refine) {
                 ws_rec<CF>(sr, t)[R_::XC + lane] += x;
             } else if (WRITE_X) {

@@ -1497,15 +1497,15 @@ static QPSet qp_settings(const m4q_qp_settings *s) {
 
 template <class CF> static int mpc_shared_doubles(int nblk) {
     // model blocks | Q | Qf | R | monomial exponents | (c multiple of 8) transposed copies of N_1..N_p for linearize()
-    return 2 * nblk * CF::C * CF::C + 2 * CF::N * CF::N + rup(CF::M * CF::M, 2) + rup(cdiv(nblk * CF::M, 2) + 1, 2) +
-           (CF::C % 8 == 0 ? 2 * (nblk - 1) * CF::C * CF::C : 0);
+    return rup(2 * nblk * CF::C * CF::C + 2 * CF::N * CF::N + rup(CF::M * CF::M, 2) + rup(cdiv(nblk * CF::M, 2) + 1, 2) +
+               (CF::C % 8 == 0 ? 2 * (nblk - 1) * CF::C * CF::C : 0), 16);   // slabs start on 128-byte boundaries
 }
 
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
     const int dd = p->d * p->d;
     if (!Slab<CF>::scratch_fits(p->p + 1, cmax(dd, CF::C))) return fail("model / plant too large for the slab scratch");
-    const int slab = rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2) +
-                     (p->model_per_member ? 2 * (p->p + 1) * CF::C * CF::C : 0);
+    const int slab = rup(rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2) +
+                             (p->model_per_member ? 2 * (p->p + 1) * CF::C * CF::C : 0), 16);
     if (p->model_mode == M4Q_MODEL_EXACT)
         return plan(mpc_kernel<CF, true>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
     return plan(mpc_kernel<CF, false>, CF::MAXW, slab, mpc_shared_doubles<CF>(p->p + 1), n, have_device, g);
