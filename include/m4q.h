@@ -218,8 +218,9 @@ int m4q_mpc_closed_loop(const m4q_mpc_problem *prob_host, int64_t N,
                         int32_t *qp_count, int32_t *counters, double *fidelity,
                         void *state, void *tables, void *stream);
 
-/* Launch geometry chosen for a problem (for reporting / roofline accounting). */
-int m4q_mpc_launch_info(const m4q_mpc_problem *prob_host, int32_t *warps_per_cta, int32_t *ctas,
+/* Launch geometry chosen for a problem and N members (N <= 0: the widest launch, which sizes the tables);
+   for reporting / roofline accounting. */
+int m4q_mpc_launch_info(const m4q_mpc_problem *prob_host, int64_t N, int32_t *warps_per_cta, int32_t *ctas,
                         int32_t *smem_bytes);
 
 /* 256-bin (or nbins) histogram of fidelities on [lo, hi]; counts [nbins] int64 are ADDED to (NCCL all-reduce later). */

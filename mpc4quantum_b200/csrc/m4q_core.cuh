@@ -1489,6 +1489,10 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
 #pragma unroll 1
             for (int rf = 0;; ++rf) {
                 const double gs = fmax(1.0, gmax);
+                // strict certificate first; once the ADMM re-seeding has been tightened below 1e-6 without settling the
+                // working set (a multiplier or a control within round-off of zero / of its bound keeps flipping), the
+                // same tests are applied with tolerances 1e4 times wider -- still a KKT point to 1e-6 relative
+                const double rx = eps <= 1e-6 ? 1e4 : 1.0;
                 bool changed = false, visible = false, unstationary = false, rough = false;
                 double umax = 0.0;
 #pragma unroll 1
@@ -1500,17 +1504,17 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                     int nm = mk;
                     umax = fmax(umax, fabs(u));
                     if (mk == 0) {
-                        if (u < lo - 1e-12) nm = 1;
-                        else if (u > hi + 1e-12) nm = 2;
+                        if (u < lo - 1e-12 * rx) nm = 1;
+                        else if (u > hi + 1e-12 * rx) nm = 2;
                         // stationarity of a free control: exact up to the round-off of the Riccati solve, unless the
                         // cost-to-go is badly scaled (long horizons with the order-1 model)
                         visible |= !(fabs(g) <= 1e-9 * gs);
                         unstationary |= !(fabs(g) <= 1e-8 * gs);
                         rough |= !(fabs(g) <= 1e-5 * gs);
                     } else if (mk == 1) {
-                        if (g < -1e-10 * gs) nm = 0;
+                        if (g < -1e-10 * rx * gs) nm = 0;
                     } else {
-                        if (g > 1e-10 * gs) nm = 0;
+                        if (g > 1e-10 * rx * gs) nm = 0;
                     }
                     if (nm != mk) {
                         s.mask[e] = nm;
@@ -1561,6 +1565,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 const int t = e / M, i = e % M;
                 s.z[e] = fmin(fmax(s.Uo[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
                 s.y[e] = s.mask[e] ? -s.kk[e] * inv_rho : 0.0;
+                if (eps <= 1e-6) s.Uo[e] = s.z[e];   // relaxed certificate: a free control may sit 1e-8 outside its bound
             }
             __syncwarp();
             break;

@@ -237,9 +237,33 @@ class ClosedLoopPlan:
         self.fidelity = _lib.empty((n,), np.float64) if self._keep['fid'] is not None else None
         self.state = _lib.empty((int(lib.m4q_mpc_state_bytes(ct.byref(self.prob), n)),), np.uint8)
 
-    def launch_info(self):
+    def fetch(self, res):
+        """Device results -> host, through pinned staging buffers owned by the plan (one asynchronous copy per array on
+        the current stream, one synchronisation).  The returned numpy arrays are views of those buffers: valid until the
+        next ``fetch`` of this plan (``mpc_ensemble(as_numpy=True)`` copies nothing else)."""
+        t = _lib.torch()
+        host = getattr(self, '_host', None)
+        if host is None:
+            host = self._host = {}
+        out = {}
+        for k in EnsembleResult.__slots__:
+            v = getattr(res, k)
+            if v is None:
+                out[k] = None
+                continue
+            buf = host.get(k)
+            if buf is None or buf.shape[0] < v.shape[0] or buf.shape[1:] != v.shape[1:] or buf.dtype != v.dtype:
+                buf = host[k] = t.empty(tuple(v.shape), dtype=v.dtype).pin_memory()
+            dst = buf[:v.shape[0]]
+            dst.copy_(v, non_blocking=True)
+            out[k] = dst
+        t.cuda.current_stream().synchronize()
+        return EnsembleResult(**{k: (None if v is None else v.numpy()) for k, v in out.items()})
+
+    def launch_info(self, n=0):
+        """Launch geometry for n members (0: the widest launch)."""
         w, c, s = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
-        _lib.check(_lib.lib().m4q_mpc_launch_info(ct.byref(self.prob), ct.byref(w), ct.byref(c), ct.byref(s)))
+        _lib.check(_lib.lib().m4q_mpc_launch_info(ct.byref(self.prob), int(n), ct.byref(w), ct.byref(c), ct.byref(s)))
         return dict(warps_per_cta=w.value, ctas=c.value, smem_bytes=s.value)
 
     def run(self, x0, H0=None, H1=None, n=None, x0_shared=False, shared_hamiltonian=False, step_begin=0,
@@ -286,7 +310,7 @@ def mpc_ensemble(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, 
     H0 = _lib.dev(experiment.H0, np.complex128)
     H1 = _lib.dev(experiment.H1, np.complex128)
     res = plan.run(x0d, H0, H1, n=n, x0_shared=shared)
-    return res.numpy() if as_numpy else res
+    return plan.fetch(res) if as_numpy else res
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -307,22 +307,44 @@ def mpc_args(cfg):
 ENSEMBLE_SEED = 20220113
 
 
-def ensemble_qubit(N, seed=ENSEMBLE_SEED, wq=2 * np.pi * 4):
-    """C2: detuning scale s ~ U[0.98, 1.02] (plant H0 = (s-1) wq sz / 2), amplitude scale a ~ U[0.9, 1.1]."""
-    rng = np.random.default_rng(seed)
-    s = rng.uniform(0.98, 1.02, N)
-    a = rng.uniform(0.9, 1.1, N)
+class _Draws:
+    """The ensemble's uniform draws, or only members [lo, hi) of them, bit for bit the same either way.
+
+    The full ensemble is a sequence of length-N ``rng.uniform`` arrays from ``np.random.default_rng(seed)``.  Each
+    double consumes one 64-bit output of PCG64, so member k of the j-th array is output j N + k of the stream:
+    ``bit_generator.advance`` jumps there, and a rank draws its own shard without materialising the other members
+    (1 M members x 8 ranks would otherwise hold 432 MB each)."""
+
+    def __init__(self, seed, N, lo=None, hi=None):
+        self.seed, self.N = seed, int(N)
+        self.lo, self.hi = (0, self.N) if lo is None else (int(lo), int(hi))
+        self.count = 0
+
+    def uniform(self, a, b):
+        rng = np.random.default_rng(self.seed)
+        rng.bit_generator.advance(self.count * self.N + self.lo)
+        self.count += 1
+        return rng.uniform(a, b, self.hi - self.lo)
+
+
+def ensemble_qubit(N, seed=ENSEMBLE_SEED, wq=2 * np.pi * 4, lo=None, hi=None):
+    """C2: detuning scale s ~ U[0.98, 1.02] (plant H0 = (s-1) wq sz / 2), amplitude scale a ~ U[0.9, 1.1].
+    lo, hi: only members [lo, hi) of the N-member ensemble (same values as slicing the full draw)."""
+    rng = _Draws(seed, N, lo, hi)
+    s = rng.uniform(0.98, 1.02)
+    a = rng.uniform(0.9, 1.1)
     H0 = 0.5 * ((s - 1) * wq)[:, None, None] * SZ
     H1 = (a[:, None, None] * (0.5 * SX))[:, None]
     return EnsembleQExperiment(H0, H1), dict(detuning_scale=s, amplitude_scale=a)
 
 
-def ensemble_transmon(N, seed=ENSEMBLE_SEED, dt=0.25):
-    """C3/C5: anharmonicity scale ~U[0.9,1.1], amplitude scale ~U[0.9,1.1], detuning ~U[-0.02,0.02] 2pi/dt on a^+a."""
-    rng = np.random.default_rng(seed)
-    k = rng.uniform(0.9, 1.1, N)
-    a_s = rng.uniform(0.9, 1.1, N)
-    det = rng.uniform(-0.02, 0.02, N) * 2 * np.pi / dt
+def ensemble_transmon(N, seed=ENSEMBLE_SEED, dt=0.25, lo=None, hi=None):
+    """C3/C5: anharmonicity scale ~U[0.9,1.1], amplitude scale ~U[0.9,1.1], detuning ~U[-0.02,0.02] 2pi/dt on a^+a.
+    lo, hi: only members [lo, hi) of the N-member ensemble (same values as slicing the full draw)."""
+    rng = _Draws(seed, N, lo, hi)
+    k = rng.uniform(0.9, 1.1)
+    a_s = rng.uniform(0.9, 1.1)
+    det = rng.uniform(-0.02, 0.02) * 2 * np.pi / dt
     alpha = -2 * np.pi * 0.1 / dt
     a = destroy(3)
     num = a.conj().T @ a
@@ -333,36 +355,38 @@ def ensemble_transmon(N, seed=ENSEMBLE_SEED, dt=0.25):
     return EnsembleQExperiment(H0, H1), dict(anharm_scale=k, amplitude_scale=a_s, detuning=det)
 
 
-def ensemble_crosstalk(N, seed=ENSEMBLE_SEED):
-    """C4: ZZ strength xi ~ U[0, 2pi 0.02], amplitude scale ~U[0.9,1.1]; plant observed through partial traces."""
-    rng = np.random.default_rng(seed)
-    xi = rng.uniform(0, 2 * np.pi * 0.02, N)
-    a_s = rng.uniform(0.9, 1.1, N)
+def ensemble_crosstalk(N, seed=ENSEMBLE_SEED, lo=None, hi=None):
+    """C4: ZZ strength xi ~ U[0, 2pi 0.02], amplitude scale ~U[0.9,1.1]; plant observed through partial traces.
+    lo, hi: only members [lo, hi) of the N-member ensemble (same values as slicing the full draw)."""
+    rng = _Draws(seed, N, lo, hi)
+    xi = rng.uniform(0, 2 * np.pi * 0.02)
+    a_s = rng.uniform(0.9, 1.1)
     H0 = 0.5 * xi[:, None, None] * np.kron(SZ, SZ)
     H1 = np.stack([a_s[:, None, None] * (0.5 * np.kron(SX, I2)), a_s[:, None, None] * (0.5 * np.kron(I2, SY))],
                   axis=1)
     return EnsembleQExperiment(H0, H1, kind='coupled'), dict(xi=xi, amplitude_scale=a_s)
 
 
-def ensemble_not_gate(N, seed=ENSEMBLE_SEED):
+def ensemble_not_gate(N, seed=ENSEMBLE_SEED, lo=None, hi=None):
     """Gate-synthesis ensemble: residual detuning delta_k ~ U[-0.05, 0.05] * 2 pi (H0 = delta_k sigma_z / 2) and drive
     amplitude scale a_k ~ U[0.9, 1.1] (H1 = a_k sigma_x / 2)."""
     from .experiment import EnsembleQExperiment
-    rng = np.random.default_rng(seed)
-    delta = rng.uniform(-0.05, 0.05, N) * 2 * np.pi
-    amp = rng.uniform(0.9, 1.1, N)
+    rng = _Draws(seed, N, lo, hi)
+    delta = rng.uniform(-0.05, 0.05) * 2 * np.pi
+    amp = rng.uniform(0.9, 1.1)
     H0 = 0.5 * delta[:, None, None] * SZ[None]
     H1 = (0.5 * amp[:, None, None] * SX[None])[:, None]
     return EnsembleQExperiment(H0, H1, kind='process'), dict(delta=delta, amp=amp)
 
 
-def transmon_model_liouvillians(N, seed=ENSEMBLE_SEED + 1, dt=0.25):
+def transmon_model_liouvillians(N, seed=ENSEMBLE_SEED + 1, dt=0.25, lo=None, hi=None):
     """Perturbed controller MODELS for the transmon (pure numpy): member k believes in the anharmonicity
     k_k alpha, k_k ~ U[0.95, 1.05], and in drive amplitudes scaled by g_k ~ U[0.97, 1.03].
     Returns the Liouvillians L [N, 3, 9, 9] of [H0, HX, HY] per member (row-major vec(rho)) and the draws."""
-    rng = np.random.default_rng(seed)
-    k = rng.uniform(0.95, 1.05, N)
-    g = rng.uniform(0.97, 1.03, N)
+    rng = _Draws(seed, N, lo, hi)
+    k = rng.uniform(0.95, 1.05)
+    g = rng.uniform(0.97, 1.03)
+    N = len(k)
     alpha = -2 * np.pi * 0.1 / dt
     a = destroy(3)
     H = np.stack([(k * alpha)[:, None, None] * proj(3, 2)[None],
@@ -373,11 +397,11 @@ def transmon_model_liouvillians(N, seed=ENSEMBLE_SEED + 1, dt=0.25):
     return L, dict(model_anharm_scale=k, model_amplitude_scale=g)
 
 
-def ensemble_transmon_models(N, order=1, dt=0.25, seed=ENSEMBLE_SEED + 1):
+def ensemble_transmon_models(N, order=1, dt=0.25, seed=ENSEMBLE_SEED + 1, lo=None, hi=None):
     """The N perturbed models discretised on the device (m4q_taylor_discretize_batched, vectorize.py:8-49 per member)
     as a ``DMDcEnsemble`` for ``mpc_ensemble``."""
     from .model import DMDcEnsemble
     from .vectorize import discretize_homogeneous_batched
-    L, params = transmon_model_liouvillians(N, seed, dt)
+    L, params = transmon_model_liouvillians(N, seed, dt, lo, hi)
     A = discretize_homogeneous_batched(L, dt, order)
     return DMDcEnsemble(9, 9, A.shape[2] - 9, A), params

@@ -71,16 +71,23 @@ def test_launch_geometry_without_a_device():
     lib = _lib.lib()
     prob = _lib.MpcProblem(c=9, m=2, p=2, d=3, horizon=16, n_steps=20, measure_freq=1, n_targ=37, sat=1.0)
     w, c, s = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
-    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 0, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
     assert 1 <= w.value <= 16 and c.value % 148 == 0 and s.value <= 227 * 1024
     shared_w, shared_s = w.value, s.value
     prob.model_per_member = 1   # every warp also holds its member's model blocks: 3 * 81 complex more per warp
-    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 0, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
     assert 1 <= w.value <= shared_w and s.value <= 227 * 1024
     assert (s.value / w.value) - (shared_s / shared_w) > 0.9 * 3 * 81 * 16
     prob.model_per_member = 0
+    # few rounds of resident warps (strong scaling): the CTA width is chosen to fill the last round
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 65536, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert w.value == shared_w == 16
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 8192, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert w.value == 14        # 8192 = 3.95 rounds of 148 x 14 instead of 3.46 rounds of 148 x 16
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 100, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert w.value == 16 and c.value == 7
     prob.horizon = 400          # does not fit the shared-memory slab: refused, not truncated
-    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == -1
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 0, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == -1
 
 
 def test_no_cpu_fallback():

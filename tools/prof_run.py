@@ -24,4 +24,4 @@ for _ in range(2):
     res = plan.run(x0, H0, H1, n=n, x0_shared=True)
     e1.record()
     torch.cuda.synchronize()
-    print('%s %d members: %.2f ms, exit codes %s, launch %s' % (name, n, e0.elapsed_time(e1), np.unique(res.exit_code.cpu().numpy()), plan.launch_info()))
+    print('%s %d members: %.2f ms, exit codes %s, launch %s' % (name, n, e0.elapsed_time(e1), np.unique(res.exit_code.cpu().numpy()), plan.launch_info(n)))
