@@ -102,6 +102,8 @@ typedef struct {
     double stream_discount;   /* OnlineDMDc.discount (model.py:28), 1 = none */
     double *stream_A;
     double *stream_P;
+    int64_t member_offset;    /* global index of member 0 of this launch: the noise stream of a member depends on its global
+                                 index only, so a sharded ensemble draws the same noise as an unsharded one */
 } m4q_mpc_problem;
 
 int m4q_version(void);

@@ -32,7 +32,7 @@ class MpcProblem(ct.Structure):
                 ('R', c_vp), ('X_targ', c_vp), ('U_targ', c_vp), ('fid_vec', c_vp), ('qp', QPSettings),
                 ('model_per_member', c_i32), ('model_mode', c_i32), ('noise_sigma', c_f64), ('noise_seed', ct.c_uint64),
                 ('streaming', c_i32), ('fidelity_sqrt', c_i32), ('stream_discount', c_f64), ('stream_A', c_vp),
-                ('stream_P', c_vp)]
+                ('stream_P', c_vp), ('member_offset', c_i64)]
 
 
 # name -> (restype, argtypes); every symbol include/m4q.h declares

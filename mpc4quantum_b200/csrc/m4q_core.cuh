@@ -121,8 +121,9 @@ template <class CF> struct Slab {
     }
     // scratch of the linearisation (2 x [p][M] derivative weights) and of the plant step (4 complex d x d):
     // aliases W, which is only live inside the Riccati factor
+    __host__ __device__ static constexpr int scratch_doubles() { return CF::FAC2 ? CF::KR * CF::LDG2 : CF::NP * CF::LDG; }
     __host__ __device__ static bool scratch_fits(int nblk, int dd) {
-        return cmax(8 * dd, 2 * CF::M * nblk) <= (CF::FAC2 ? CF::KR * CF::LDG2 : CF::NP * CF::LDG);
+        return cmax(8 * dd, 2 * CF::M * nblk) <= scratch_doubles();
     }
     // dd = plant state length in complex numbers (d*d)
     __host__ __device__ static int layout(Slab *s, double *base, int H, int nblk, int dd) {

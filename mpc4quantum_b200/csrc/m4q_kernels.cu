@@ -215,6 +215,103 @@ __device__ double fidelity_of(int mode, int d, const double2 *w, const double2 *
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Measurement noise (experiment.py:193-194, :212): counter-based generator Philox4x32-10, key = the 64-bit seed,
+// counter = (member lo, member hi, MPC step, component): one call gives the two N(0,1) deviates of a complex
+// component (Box-Muller on two 53-bit uniforms).  Independent of the launch geometry and of the GPU count.
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0;
+        c[1] = n1;
+        c[2] = n2;
+        c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double2 normal_pair(uint64_t seed, long long member, int step, int comp) {
+    uint32_t c[4] = {(uint32_t)member, (uint32_t)((unsigned long long)member >> 32), (uint32_t)step, (uint32_t)comp};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * 0x1.0p-53 + 0x1.0p-54;
+    const double u2 = (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * 0x1.0p-53;
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return make_double2(r * cs, r * sn);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Streaming model of one member (OnlineDMDc, model.py:216-313): A [c][dz], P [dz][dz] complex in global memory,
+// dz = c (p + 1); z = [x; phi_1 x; ..; phi_p x] is built in shared memory (zs, dz complex).
+//   stream_predict:  out = A z                                         (model.py:81-93 with the member's A)
+//   stream_update:   gamma = 1 / (1 + z^T P z);  A += gamma (y - A z)(P z)^T;  P = (P - gamma P z (P z)^T) / discount
+// (plain transposes, as the reference writes them).  pz: dz complex of shared scratch.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF>
+__device__ void stream_build_z(const double *x_real, const double *phi, int nblk, double2 *zs, int lane) {
+    constexpr int C = CF::C;
+#pragma unroll 1
+    for (int e = lane; e < nblk * C; e += 32) {
+        const int kb = e / C, r = e % C;
+        const double ph = kb == 0 ? 1.0 : phi[kb];
+        zs[e] = make_double2(ph * x_real[r], ph * x_real[C + r]);
+    }
+    __syncwarp();
+}
+template <class CF>
+__device__ double2 stream_row_dot(const double2 *row, const double2 *zs, int dz) {
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int j = 0; j < dz; ++j) acc = cfma(row[j], zs[j], acc);
+    return acc;
+}
+template <class CF>
+__device__ void stream_update(double2 *A, double2 *P, const double2 *zs, const double *y_real, int dz, double discount,
+                              double2 *pz, double2 *red, int lane) {
+    constexpr int C = CF::C;
+    // P z (rows over lanes) and z^T P z
+    double2 part = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int i = lane; i < dz; i += 32) {
+        const double2 v = stream_row_dot<CF>(P + (size_t)i * dz, zs, dz);
+        pz[i] = v;
+        part = cfma(zs[i], v, part);
+    }
+    part.x = warp_sum(part.x);
+    part.y = warp_sum(part.y);
+    // gamma = 1 / (1 + z^T P z), complex
+    const double dr = 1.0 + part.x, di = part.y, dn = dr * dr + di * di;
+    const double2 gamma = make_double2(dr / dn, -di / dn);
+    __syncwarp();
+    // A += gamma (y - A z) (P z)^T : lane r < C owns row r
+    if (lane < C) {
+        double2 *row = A + (size_t)lane * dz;
+        const double2 az = stream_row_dot<CF>(row, zs, dz);
+        const double2 err = cmul(gamma, make_double2(y_real[lane] - az.x, y_real[C + lane] - az.y));
+#pragma unroll 1
+        for (int j = 0; j < dz; ++j) row[j] = cfma(err, pz[j], row[j]);
+    }
+    // P = (P - gamma (P z)(P z)^T) / discount : rows over lanes
+    const double inv = 1.0 / discount;
+#pragma unroll 1
+    for (int i = lane; i < dz; i += 32) {
+        double2 *row = P + (size_t)i * dz;
+        const double2 gi = cmul(gamma, pz[i]);
+#pragma unroll 1
+        for (int j = 0; j < dz; ++j) {
+            const double2 d = cmul(gi, pz[j]);
+            row[j] = make_double2((row[j].x - d.x) * inv, (row[j].y - d.y) * inv);
+        }
+    }
+    (void)red;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // The closed loop kernel
 // ---------------------------------------------------------------------------------------------------------
 struct MpcArgs {
@@ -240,6 +337,12 @@ struct MpcArgs {
     int slab_doubles, shared_doubles;
     int model_per_member;   // A_blocks is [n_members][nblk][C][C]: every member controls with its own model
     double *ws_exact;       // EXACT: per resident warp, the stage matrices A_t = expm(G(u_t) dt)  [H][C][C] complex
+    double noise_sigma;
+    unsigned long long noise_seed;
+    long long member_offset;   // global index of member 0 of this launch (noise streams do not depend on the sharding)
+    int streaming, fidelity_sqrt;
+    double stream_discount;
+    double2 *stream_A, *stream_P;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -444,6 +547,12 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                     s.hi0[lane] = hi;
                 }
                 __syncwarp();
+                // an empty stage-0 box (reference control outside the saturation range by more than du): the reference's
+                // solver reports the problem infeasible and mpc() leaves with exit code 3 (mpc.py:200-203)
+                if (__any_sync(FULL, lane < M && s.lo0[lane < M ? lane : 0] > s.hi0[lane < M ? lane : 0])) {
+                    exit_code = 3;
+                    break;
+                }
 
                 int n_iter = 0;
                 bool done = false;
@@ -524,6 +633,13 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                             if (a.lift_mode == M4Q_LIFT_PROCESS) left_multiply(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
                             else conjugate(xmeas, scr2 + 2 * dd, d, scr2 + dd, lane);
                         }
+                        if (a.noise_sigma > 0.0 && lane < dd) {
+                            // measurement noise; the plant goes on from the noisy record, as the reference's does
+                            // (experiment.py:212 feeds mpc.py:259)
+                            const double2 nz = normal_pair(a.noise_seed, a.member_offset + k, step, lane);
+                            xmeas[lane].x = fma(a.noise_sigma, nz.x, xmeas[lane].x);
+                            xmeas[lane].y = fma(a.noise_sigma, nz.y, xmeas[lane].y);
+                        }
                         if (lane < dd) xcur[lane] = xmeas[lane];
                         __syncwarp();
                     } else {
@@ -539,13 +655,46 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                             s.scr[lane] = phi;
                         }
                         __syncwarp();
-                        const double fx = apply_A<CF>(model, s.scr, 0, s.x0, lane);
-                        __syncwarp();
-                        if (lane < N) s.va[lane] = fx;
+                        if (a.streaming) {
+                            // the member's own, updated model predicts (model.py:81-93 after fit_iteration rebinds A)
+                            double2 *zs = reinterpret_cast<double2 *>(s.scr + MAXBLK);
+                            const int dz = a.nblk * C;
+                            stream_build_z<CF>(s.x0, s.scr, a.nblk, zs, lane);
+                            if (lane < C) {
+                                const double2 v = stream_row_dot<CF>(a.stream_A + ((size_t)k * C + lane) * dz, zs, dz);
+                                s.va[lane] = v.x;
+                                s.va[C + lane] = v.y;
+                            }
+                        } else {
+                            const double fx = apply_A<CF>(model, s.scr, 0, s.x0, lane);
+                            __syncwarp();
+                            if (lane < N) s.va[lane] = fx;
+                        }
                         __syncwarp();
                         proj_state<CF>(a.lift_mode, d, s.va, xcur, lane);
                     }
                     if (lane < dd) xs_k[(size_t)lane * (S + 1) + step + 1] = xcur[lane];
+                    if (a.streaming) {
+                        // online model update with the transition just observed (mpc.py:281-285, model.py:295-313)
+                        __syncwarp();
+                        if (lane < a.nblk) {
+                            double phi = 1.0;
+                            if (lane > 0)
+                                for (int l = 0; l < M; ++l) {
+                                    const double ul = s.Uo[l];
+#pragma unroll 1
+                                    for (int q = 0; q < pow[(lane - 1) * M + l]; ++q) phi *= ul;
+                                }
+                            s.scr[lane] = phi;
+                        }
+                        __syncwarp();
+                        const int dz = a.nblk * C;
+                        double2 *zs = reinterpret_cast<double2 *>(s.scr + MAXBLK), *pz = zs + dz;
+                        stream_build_z<CF>(s.x0, s.scr, a.nblk, zs, lane);
+                        lift_state<CF>(a.lift_mode, d, xcur, s.va, lane);
+                        stream_update<CF>(a.stream_A + (size_t)k * C * dz, a.stream_P + (size_t)k * dz * dz, zs, s.va, dz,
+                                          a.stream_discount, pz, pz + dz, lane);
+                    }
                 }
 
                 // shift the guesses (mpc.py:271-272) and, with them, the ADMM warm start
@@ -590,7 +739,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
         }
         if (a.fidelity && !a.external_plant && a.fid_vec) {
             const double f = fidelity_of<CF>(a.lift_mode, d, a.fid_vec, xcur, s.va, lane);
-            if (lane == 0) a.fidelity[k] = f;
+            if (lane == 0) a.fidelity[k] = a.fidelity_sqrt ? sqrt(fmax(f, 0.0)) : f;
         }
         if (a.state) {
             double *st = a.state + (size_t)k * persist;
@@ -1533,6 +1682,8 @@ template <class CF> static int mpc_shared_doubles(int nblk) {
 template <class CF> static int mpc_geometry(const m4q_mpc_problem *p, long long n, bool have_device, Geometry *g) {
     const int dd = p->d * p->d;
     if (!Slab<CF>::scratch_fits(p->p + 1, cmax(dd, CF::C))) return fail("model / plant too large for the slab scratch");
+    if (p->streaming && MAXBLK + 4 * (p->p + 1) * CF::C > Slab<CF>::scratch_doubles())
+        return fail("streaming model too large for the slab scratch (z and P z, 2 x c (p + 1) complex)");
     const int slab = rup(rup(Slab<CF>::doubles(p->horizon, p->p + 1, cmax(dd, CF::C)), 2) +
                              (p->model_per_member ? 2 * (p->p + 1) * CF::C * CF::C : 0), 16);
     if (p->model_mode == M4Q_MODEL_EXACT)
@@ -1565,7 +1716,8 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
         size_t ws_bytes = (size_t)g.ctas * g.warps * ws_doubles<CF>(p->horizon) * sizeof(double);
         if (max_persist > 0 && max_window > 0) {
             const size_t want = ws_bytes < (size_t)max_persist ? ws_bytes : (size_t)max_persist;
-            static size_t reserved = 0;
+            static size_t reserved_per_device[64] = {0};     // the limit is a per-device setting
+            size_t &reserved = reserved_per_device[dev & 63];
             if (want > reserved && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) reserved = want;
             cudaStreamAttrValue attr;
             memset(&attr, 0, sizeof(attr));
@@ -1942,6 +2094,16 @@ int m4q_mpc_closed_loop(const m4q_mpc_problem *p, int64_t N, const double *x0, i
     a.counters = counters;
     a.fidelity = fidelity;
     a.state = (double *)state;
+    a.noise_sigma = external_plant ? 0.0 : p->noise_sigma;
+    a.noise_seed = p->noise_seed;
+    a.member_offset = p->member_offset;
+    a.streaming = external_plant ? 0 : p->streaming;
+    a.fidelity_sqrt = p->fidelity_sqrt;
+    a.stream_discount = p->stream_discount > 0 ? p->stream_discount : 1.0;
+    a.stream_A = (double2 *)p->stream_A;
+    a.stream_P = (double2 *)p->stream_P;
+    if (a.streaming && (!a.stream_A || !a.stream_P)) return fail("streaming needs the per-member stream_A / stream_P buffers");
+    if (a.streaming && p->model_mode == M4Q_MODEL_EXACT) return fail("streaming updates belong to the Taylor (DMDc) model");
     M4Q_DISPATCH(p->c, p->m, { return launch_mpc<CF>(p, N, a, (cudaStream_t)stream); });
     return 0;
 }

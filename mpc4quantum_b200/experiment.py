@@ -56,8 +56,17 @@ class Experiment(ABC):
 
 
 def _controls_on_grid(us, ts):
-    """Control per segment [n_seg, m]: us(ts[i]) for a callable (interp1d kind='previous'), column i otherwise."""
+    """Control per segment [n_seg, m]: us(ts[i]) for a callable, column i of an array otherwise.
+
+    The plant holds the control constant over a segment (zero-order hold), which is exactly what ``mpc()`` hands over:
+    an ``interp1d(..., kind='previous')`` (mpc.py:258).  The reference integrates whatever interpolant it is given
+    (qutip splines an ndarray); an interp1d of any other kind is refused instead of being silently sampled as a
+    zero-order hold.  Any other callable, and an array, are sampled at the left end of every segment."""
     n_seg = len(ts) - 1
+    kind = getattr(us, '_kind', None)
+    if kind is not None and kind != 'previous':
+        raise NotImplementedError("the device plant holds the control constant over a segment: pass "
+                                  "interp1d(kind='previous') (mpc.py:258), got kind=%r" % (kind,))
     if callable(us):
         cols = [np.real(np.asarray(us(ts[i]))).reshape(-1) for i in range(n_seg)]
         return np.array(cols, dtype=float).reshape(n_seg, -1)
@@ -100,10 +109,22 @@ class QExperiment(Experiment):
     def f(self, t, x, u):
         return self.H0 * x + np.sum([H1 * x * u1 for H1, u1 in zip(self.H1_list, u)], axis=0)
 
-    def set_sigma(self, sigma):
+    def set_sigma(self, sigma, seed=None):
+        """Measurement noise (experiment.py:193-194): sigma (N(0,1) + i N(0,1)) on every returned state.  Inside the
+        fused loop the noise comes from a counter-based generator keyed by `seed` (drawn from numpy's global generator
+        at call time when None, so that ``np.random.seed`` governs reproducibility as it does in the reference)."""
         self._sigma = sigma
+        self._noise_seed = seed
+
+    _DEVICE_KEYS = ('rho0', 'tlist', 'H')      # what simulate() itself sets in the reference (experiment.py:203-208)
 
     def set(self, key, value):
+        """Keyword for qutip's mesolve in the reference (experiment.py:196-200).  The device plant is the closed-system
+        propagator of H0 + sum u_k H1_k: collapse operators, expectation operators, solver options or extra arguments
+        cannot be honoured and are refused instead of being ignored."""
+        if key not in self._DEVICE_KEYS:
+            raise NotImplementedError("QExperiment.set(%r, ...): the device plant integrates the closed system only "
+                                      "(no c_ops / e_ops / options / args)" % (key,))
         self._me_args[key] = value
 
     def simulate(self, x0, ts, us):
@@ -180,6 +201,10 @@ class QSynthesis(Experiment):
         return self.H0 * x + np.sum([H1 * x * u1 for H1, u1 in zip(self.H1_list, u)], axis=0)
 
     def set(self, key, value):
+        """Keyword for qutip's propagator in the reference (experiment.py:351-355); only what ``simulate`` itself sets
+        is accepted -- see ``QExperiment.set``."""
+        if key not in ('H', 't'):
+            raise NotImplementedError("QSynthesis.set(%r, ...): the device plant is the closed-system propagator" % (key,))
         self._prop_args[key] = value
 
     @staticmethod
@@ -264,6 +289,7 @@ class EnsembleQExperiment:
         self.H0 = H0
         self.H1 = H1
         self.kind = kind
+        self._sigma, self._noise_seed = 0.0, None
         self.lift_mode, self._cls = _KINDS[kind]
         self.lift = self._cls.lift
         self.proj = self._cls.proj
@@ -289,7 +315,15 @@ class EnsembleQExperiment:
         return self._cls(np.array(H0), [np.array(h) for h in H1])
 
     def slice(self, lo, hi):
-        return EnsembleQExperiment(self.H0[lo:hi], self.H1[lo:hi], self.kind)
+        out = EnsembleQExperiment(self.H0[lo:hi], self.H1[lo:hi], self.kind)
+        out._sigma, out._noise_seed = self._sigma, self._noise_seed
+        out.member_offset = getattr(self, 'member_offset', 0) + lo
+        return out
+
+    def set_sigma(self, sigma, seed=None):
+        """Measurement noise of every member (``QExperiment.set_sigma``); the stream of member k depends on
+        (seed, global index of k, MPC step, component) only."""
+        self._sigma, self._noise_seed = float(sigma), seed
 
     def simulate(self, x0, u_seg, dt, return_propagators=False):
         """x0 [N, d*d], u_seg [N, n_seg, m] -> device tensor [N, n_seg, d*d]."""

@@ -129,7 +129,7 @@ def iqp_line_search(Q_ls, R_ls, X_htarg, U_htarg, X_guess, U_guess, X_opt, U_opt
 # ----------------------------------------------------------------------------------------------------------
 class EnsembleResult:
     """Outputs of mpc_ensemble (device tensors unless converted with .numpy())."""
-    __slots__ = ('xs', 'us', 'exit_code', 'steps_done', 'qp_count', 'counters', 'fidelity')
+    __slots__ = ('xs', 'us', 'exit_code', 'steps_done', 'qp_count', 'counters', 'fidelity', 'model_A', 'model_P')
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -267,15 +267,48 @@ class ClosedLoopPlan:
         return dict(warps_per_cta=w.value, ctas=c.value, smem_bytes=s.value)
 
     def run(self, x0, H0=None, H1=None, n=None, x0_shared=False, shared_hamiltonian=False, step_begin=0,
-            step_end=None, stream=None):
-        """Enqueue the closed loop for n members.  x0/H0/H1 are CUDA tensors (complex128)."""
+            step_end=None, stream=None, noise_sigma=0.0, noise_seed=0, member_offset=0, streaming=None,
+            fidelity_sqrt=False):
+        """Enqueue the closed loop for n members.  x0/H0/H1 are CUDA tensors (complex128).
+
+        A plan owns ONE set of tables (with the atomic work counter of the launch) and ONE set of output buffers: keep at
+        most one launch of a plan in flight; use one plan per stream for concurrent launches.
+        Results of members that stop early (exit codes 1/2/3) are zero beyond ``steps_done``.
+        streaming = (A [n, c, c (p+1)], P [n, dz, dz], discount): per-member OnlineDMDc state, updated in place."""
         n = self.capacity if n is None else int(n)
         if self.n_models and n > self.n_models:
             raise ValueError('%d members but only %d models' % (n, self.n_models))
         if n > self.capacity:
             self._alloc(n)
+        if not self.external and n > 0:
+            if H0 is None or H1 is None:
+                raise ValueError('plant Hamiltonians H0, H1 are required')
+            if H0.shape[-1] != self.d or H0.shape[-2] != self.d:
+                raise ValueError('H0 is %s, the plan was built for d = %d' % (tuple(H0.shape), self.d))
+            if H1.shape[-1] != self.d or H1.shape[-3] != self.m:
+                raise ValueError('H1 is %s, expected [.., dim_u = %d, %d, %d] (one drive Hamiltonian per control)'
+                                 % (tuple(H1.shape), self.m, self.d, self.d))
+            if not shared_hamiltonian and (H0.shape[0] < n or H1.shape[0] < n):
+                raise ValueError('%d members but %d / %d Hamiltonians' % (n, H0.shape[0], H1.shape[0]))
+        if n > 0 and x0.shape[-1] != self.xdim:
+            raise ValueError('x0 has %d entries per member, the plant state has %d' % (x0.shape[-1], self.xdim))
+        if n > 0 and not x0_shared and x0.shape[0] < n:
+            raise ValueError('%d members but %d initial states (pass x0_shared=True for one shared state)' % (n, x0.shape[0]))
         step_end = self.S if step_end is None else step_end
         partial = step_begin > 0 or step_end < self.S
+        if step_begin == 0:
+            self.xs[:n].zero_()
+            self.us[:n].zero_()
+            self.qp_count[:n].zero_()
+        self.prob.noise_sigma, self.prob.noise_seed = float(noise_sigma), int(noise_seed) & (2 ** 64 - 1)
+        self.prob.member_offset = int(member_offset)
+        self.prob.fidelity_sqrt = int(bool(fidelity_sqrt))
+        if streaming is not None:
+            sA, sP, disc = streaming
+            self.prob.streaming, self.prob.stream_discount = 1, float(disc)
+            self.prob.stream_A, self.prob.stream_P = sA.data_ptr(), sP.data_ptr()
+        else:
+            self.prob.streaming, self.prob.stream_A, self.prob.stream_P = 0, None, None
         _lib.check(_lib.lib().m4q_mpc_closed_loop(
             ct.byref(self.prob), n, _lib.ptr(x0), int(x0_shared), _lib.ptr(H0), _lib.ptr(H1), int(shared_hamiltonian),
             int(step_begin), int(step_end), int(self.external), _lib.ptr(self.xs), _lib.ptr(self.us),
@@ -284,17 +317,40 @@ class ClosedLoopPlan:
             _lib.ptr(self.tables), _lib.stream_ptr(stream)))
         return EnsembleResult(xs=self.xs[:n], us=self.us[:n], exit_code=self.exit_code[:n],
                               steps_done=self.steps_done[:n], qp_count=self.qp_count[:n], counters=self.counters[:n],
-                              fidelity=None if self.fidelity is None else self.fidelity[:n])
+                              fidelity=None if self.fidelity is None else self.fidelity[:n],
+                              model_A=None if streaming is None else streaming[0][:n],
+                              model_P=None if streaming is None else streaming[1][:n])
+
+
+def _noise_of(experiment):
+    """(sigma, seed) of an experiment with set_sigma(); a missing seed is drawn from numpy's global generator."""
+    sigma = float(getattr(experiment, '_sigma', 0) or 0)
+    if not sigma:
+        return 0.0, 0
+    seed = getattr(experiment, '_noise_seed', None)
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+    return sigma, int(seed)
 
 
 def mpc_ensemble(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat=None, du=None, max_iter=100,
-                 warm_start=True, fid_target=None, exit_infidelity=0.0, settings=None, plan=None, as_numpy=True):
+                 warm_start=True, fid_target=None, exit_infidelity=0.0, settings=None, plan=None, as_numpy=True,
+                 streaming=False, fidelity_convention='prob'):
     """The loop of mpc.py:128-304 for every plant of an ``EnsembleQExperiment`` (one warp per member).
 
     x0 is one plant state (shared) or [N, d*d].  Returns an ``EnsembleResult``: xs [N, d*d, S+1], us [N, m, S],
     exit_code [N] (reference codes), steps_done [N], qp_count [N, S], counters [N, 4], fidelity [N] if a target
     vector is given.
-    """
+
+    streaming=True (mpc.py:281-285) with an ``OnlineDMDc`` model: every member starts from the model's (A, P) and
+    runs its own rank-1 updates on the device after every step (model.py:295-313); the final operators come back as
+    ``model_A [N, c, c (p+1)]`` and ``model_P``.  As in the reference the controller keeps the operators it was built
+    with; the updated ones drive the model steps between measurements (``clock.measure_freq > 1``).
+    fidelity_convention: 'prob' = Re<target, x> (<psi|rho|psi> for a pure target), 'sqrt' = its square root, which is
+    what the reference's figures plot (qutip.fidelity, tests/test_mpc4quantum.py:590, :691).
+    experiment.set_sigma(sigma, seed): measurement noise inside the fused loop (experiment.py:193-194, :212)."""
+    if fidelity_convention not in ('prob', 'sqrt'):
+        raise ValueError("fidelity_convention is 'prob' or 'sqrt'")
     n = len(experiment)
     if plan is None:
         plan = ClosedLoopPlan(dim_u, order, X_targ, U_targ, clock, model, Q, R, Qf, sat, du, experiment.d,
@@ -309,7 +365,20 @@ def mpc_ensemble(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, 
     x0d = _lib.dev(x0.reshape(1, -1) if shared else x0, np.complex128)
     H0 = _lib.dev(experiment.H0, np.complex128)
     H1 = _lib.dev(experiment.H1, np.complex128)
-    res = plan.run(x0d, H0, H1, n=n, x0_shared=shared)
+    stream_state = None
+    if streaming:
+        if not (hasattr(model, 'P') and hasattr(model, 'A')) or plan.exact:
+            raise NotImplementedError('streaming inside the fused ensemble loop needs an OnlineDMDc model (A, P); '
+                                      'DiscrepDMDc runs through mpc(streaming=True) on the host-stepped path')
+        t = _lib.torch()
+        A0 = _lib.dev(np.asarray(model.A, dtype=complex), np.complex128)
+        P0 = _lib.dev(np.asarray(model.P, dtype=complex), np.complex128)
+        stream_state = (A0.unsqueeze(0).repeat(n, 1, 1).contiguous(), P0.unsqueeze(0).repeat(n, 1, 1).contiguous(),
+                        float(getattr(model, 'discount', 1)))
+    sigma, seed = _noise_of(experiment)
+    res = plan.run(x0d, H0, H1, n=n, x0_shared=shared, noise_sigma=sigma, noise_seed=seed,
+                   member_offset=getattr(experiment, 'member_offset', 0), streaming=stream_state,
+                   fidelity_sqrt=fidelity_convention == 'sqrt')
     return plan.fetch(res) if as_numpy else res
 
 
@@ -320,8 +389,7 @@ def _device_plant(experiment):
     from .experiment import QExperiment, QProcess, QSynthesis
     if isinstance(experiment, QProcess):
         return type(experiment).simulate is QSynthesis.simulate
-    return isinstance(experiment, QExperiment) and not experiment._sigma and \
-        type(experiment).simulate is QExperiment.simulate
+    return isinstance(experiment, QExperiment) and type(experiment).simulate is QExperiment.simulate
 
 
 def mpc(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat=None, du=None, max_iter=100,
@@ -333,9 +401,10 @@ def mpc(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sa
     if sat is None:
         raise TypeError('sat is mandatory: the reference fails at optimize.py:43 without it')
     x0 = np.asarray(x0, dtype=complex).reshape(-1)
-    if _device_plant(experiment) and exit_condition is None and not streaming:
+    fused_stream = streaming and hasattr(model, 'P') and not isinstance(model, ExactModel)     # OnlineDMDc
+    if _device_plant(experiment) and exit_condition is None and (not streaming or fused_stream):
         return _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,
-                          warm_start)
+                          warm_start, streaming)
     return _mpc_host_stepped(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter,
                              exit_condition, warm_start, streaming)
 
@@ -356,8 +425,13 @@ def _finish(xs, us, steps_done, exit_code, clock, model):
     return [xs[:, :idx + 1], us[:, :idx] if idx > 0 else None], model, exit_code
 
 
-def _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter, warm_start):
+def _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R, Qf, sat, du, max_iter, warm_start,
+               streaming=False):
     d = experiment.H0.shape[0]
+    if len(experiment.H1_list) != dim_u:
+        raise IndexError('dim_u = %d but the experiment has %d drive Hamiltonians' % (dim_u, len(experiment.H1_list)))
+    if x0.shape[0] != (d ** 4 if experiment.lift_mode == _lib.LIFT_PROCESS else d * d):
+        raise ValueError('x0 has %d entries, the plant state has %d' % (x0.shape[0], d * d))
     plan = ClosedLoopPlan(dim_u, order, X_targ, U_targ, clock, model, Q, R, Qf, sat, du, d, experiment.lift_mode,
                           max_iter, warm_start, capacity=1)
     H0 = _lib.dev(experiment.H0[None], np.complex128)
@@ -365,7 +439,16 @@ def _mpc_fused(x0, dim_u, order, X_targ, U_targ, clock, experiment, model, Q, R,
     process = experiment.lift_mode == _lib.LIFT_PROCESS
     if process:     # the kernel carries the propagator; mpc() speaks process vectors (experiment.py:371-401)
         x0 = np.asarray(experiment.to_unitary(x0), dtype=complex)
-    res = plan.run(_lib.dev(x0[None], np.complex128), H0, H1, n=1).numpy()
+    stream_state = None
+    if streaming:
+        stream_state = (_lib.dev(np.asarray(model.A, dtype=complex)[None], np.complex128),
+                        _lib.dev(np.asarray(model.P, dtype=complex)[None], np.complex128), float(model.discount))
+    sigma, seed = _noise_of(experiment)
+    res = plan.run(_lib.dev(x0[None], np.complex128), H0, H1, n=1, noise_sigma=sigma, noise_seed=seed,
+                   streaming=stream_state).numpy()
+    if streaming:       # fit_iteration rebinds the operators (model.py:305-306); so does this
+        model.A, model.P = res.model_A[0], res.model_P[0]
+        model._iteration += int(res.steps_done[0])
     xs = res.xs[0]
     if process:
         xs = np.array([experiment.from_unitary(col) for col in xs.T]).T

@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.QPSettings) == 48
     # 12 ints, 4 doubles, 8 pointers, the settings, model_per_member + model_mode, noise (2 x 8), streaming +
-    # fidelity_sqrt, discount, two stream pointers
-    assert ctypes.sizeof(_lib.MpcProblem) == 12 * 4 + 4 * 8 + 8 * 8 + 48 + 8 + 16 + 8 + 8 + 16
+    # fidelity_sqrt, discount, two stream pointers, member_offset
+    assert ctypes.sizeof(_lib.MpcProblem) == 12 * 4 + 4 * 8 + 8 * 8 + 48 + 8 + 16 + 8 + 8 + 16 + 8
     assert _lib.MpcProblem.dt.offset == 48 and _lib.MpcProblem.A_blocks.offset == 80
     assert _lib.MpcProblem.model_per_member.offset == 192 and _lib.MpcProblem.noise_sigma.offset == 200
     assert _lib.MpcProblem.stream_P.offset == 240
