@@ -115,6 +115,7 @@ template <class CF> struct Slab {
     double *recring;   // 2-slot ring of whole stage records for the vector sweeps (aliases the factor scratch)
     double *xd;        // 2 N doubles of scratch for the general-cost adjoint sweep
     int *mask;
+    int *flips;        // how often a control has been released from the working set during the current QP solve
 
     __host__ __device__ static int doubles(int H, int nblk, int dd) {
         return layout(nullptr, nullptr, H, nblk, dd);
@@ -172,6 +173,8 @@ template <class CF> struct Slab {
         double *mk = nullptr;
         take(&mk, cdiv(H * M, 2));
         if (s) s->mask = reinterpret_cast<int *>(mk);
+        take(&mk, cdiv(H * M, 2));
+        if (s) s->flips = reinterpret_cast<int *>(mk);
         return o;
     }
     // the part that must survive between launches in host-stepped mode: Xg | Ug | z | y | xcur | xmeas
@@ -1341,43 +1344,18 @@ __device__ __noinline__ double adjoint_gradient(SlabRef sr, const QPData &qp_in,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The QP (optimize.py:12-60).  Two building blocks share the Riccati kernels:
-//   * ADMM on the control box (u = z, z in [lo, hi]); u-update = equality-constrained LQ problem solved exactly by
-//     the time-varying Riccati recursion; convergence by warp vote over each lane's slice of the residuals.
-//   * primal-dual active set ("polish"): controls in the working set are pinned to their bound and folded into
-//     the dynamics, one masked Riccati factor + solve gives the equality-constrained optimum, and an adjoint
-//     gradient certifies the KKT conditions (multiplier signs on pinned controls, feasibility of free ones) or
-//     updates the set.  The certificate is a full KKT check: stationarity of the free controls (1e-8 relative),
-//     primal feasibility (1e-12), multiplier signs (1e-10 relative).
-// Tight mode (polish = 1): the working set is warm-started from the previous solve's (z, y) -- the previous SQP
-// iterate or the shifted previous MPC step -- and the active-set rounds run first; an ADMM block (which needs no
-// guess) is the fallback that re-seeds the set when the rounds do not certify.  admm_first = 1 always runs the ADMM
-// block before the rounds.  polish = 0 is plain ADMM to residual eps (OSQP-equivalent mode).
-// In: slab {B, D, phi, x0, lo0, hi0, z, y(warm)}.  Out: Xo, Uo; z, y updated.  Returns status 0 / 2 / 3.
+// One ADMM block on the control box (u = z, z in [lo, hi]) down to residual eps; cold in the tight mode (it only
+// re-seeds the working set when the active-set rounds do not settle), hence a function of its own: the hot loop of
+// qp_solve stays small for the instruction cache.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF, bool FUSED>
-__device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, const QPSet &set, int lane, Counters &cnt) {
-    constexpr int N = CF::N, M = CF::M;
+__device__ __noinline__ void admm_block(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, const QPSet &set,
+                                        double eps, int lane, Counters &cnt) {
+    constexpr int M = CF::M;
     const Slab<CF> s = slab_view<CF>(sr);
-    const StageOps ops = localize<FUSED>(ops_in);
     const QPData qp = localize<FUSED>(qp_in);
-    const int H = sr.H;
-    const int HM = H * M;
+    const int HM = sr.H * M;
     const double rho_half = 0.5 * set.rho;
-    // clip the warm start into the current box
-#pragma unroll 1
-    for (int e = lane; e < HM; e += 32) {
-        const int t = e / M, i = e % M;
-        s.z[e] = fmin(fmax(s.z[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
-    }
-    __syncwarp();
-    cnt.solves++;
-    double eps = set.eps;
-    int status = 0;
-    bool x_nonfinite = false;   // a non-finite state of the reported rollout (it propagates to x_H)
-    bool run_admm = !set.polish || set.admm_first;
-    for (;;) {
-        if (run_admm) {
 #pragma unroll 1
             for (int e = lane; e < HM; e += 32) s.mask[e] = 0;   // the sweeps read the working set: none in ADMM
             __syncwarp();
@@ -1440,6 +1418,46 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 __syncwarp();
             }
         }
+
+// ---------------------------------------------------------------------------------------------------------
+// The QP (optimize.py:12-60).  Two building blocks share the Riccati kernels:
+//   * ADMM on the control box (u = z, z in [lo, hi]); u-update = equality-constrained LQ problem solved exactly by
+//     the time-varying Riccati recursion; convergence by warp vote over each lane's slice of the residuals.
+//   * primal-dual active set ("polish"): controls in the working set are pinned to their bound and folded into
+//     the dynamics, one masked Riccati factor + solve gives the equality-constrained optimum, and an adjoint
+//     gradient certifies the KKT conditions (multiplier signs on pinned controls, feasibility of free ones) or
+//     updates the set.  The certificate is a full KKT check: stationarity of the free controls (1e-8 relative),
+//     primal feasibility (1e-12), multiplier signs (1e-10 relative).
+// Tight mode (polish = 1): the working set is warm-started from the previous solve's (z, y) -- the previous SQP
+// iterate or the shifted previous MPC step -- and the active-set rounds run first; an ADMM block (which needs no
+// guess) is the fallback that re-seeds the set when the rounds do not certify.  admm_first = 1 always runs the ADMM
+// block before the rounds.  polish = 0 is plain ADMM to residual eps (OSQP-equivalent mode).
+// In: slab {B, D, phi, x0, lo0, hi0, z, y(warm)}.  Out: Xo, Uo; z, y updated.  Returns status 0 / 2 / 3.
+// ---------------------------------------------------------------------------------------------------------
+template <class CF, bool FUSED>
+__device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in, const QPSet &set, int lane, Counters &cnt) {
+    constexpr int N = CF::N, M = CF::M;
+    const Slab<CF> s = slab_view<CF>(sr);
+    const StageOps ops = localize<FUSED>(ops_in);
+    const QPData qp = localize<FUSED>(qp_in);
+    const int H = sr.H;
+    const int HM = H * M;
+    const double rho_half = 0.5 * set.rho;
+    // clip the warm start into the current box
+#pragma unroll 1
+    for (int e = lane; e < HM; e += 32) {
+        const int t = e / M, i = e % M;
+        s.z[e] = fmin(fmax(s.z[e], box_lo(s, qp.sat, t, i)), box_hi(s, qp.sat, t, i));
+        s.flips[e] = 0;
+    }
+    __syncwarp();
+    cnt.solves++;
+    double eps = set.eps;
+    int status = 0;
+    bool x_nonfinite = false;   // a non-finite state of the reported rollout (it propagates to x_H)
+    bool run_admm = !set.polish || set.admm_first;
+    for (;;) {
+        if (run_admm) admm_block<CF, FUSED>(sr, ops_in, qp_in, set, eps, lane, cnt);
         if (!set.polish) {
             // OSQP-equivalent mode: report the feasible iterate z and its rollout
 #pragma unroll 1
@@ -1512,10 +1530,18 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                         visible |= !(fabs(g) <= 1e-9 * gs);
                         unstationary |= !(fabs(g) <= 1e-8 * gs);
                         rough |= !(fabs(g) <= 1e-5 * gs);
-                    } else if (mk == 1) {
-                        if (g < -1e-10 * rx * gs) nm = 0;
                     } else {
-                        if (g > 1e-10 * rx * gs) nm = 0;
+                        // A weakly active bound (multiplier within the evaluation noise of zero) would otherwise be
+                        // released, violated, pinned and released again for ever: a control that has come back twice
+                        // stays pinned unless its multiplier is negative beyond that noise.
+                        const double gn = mk == 1 ? -g : g;       // > 0: the multiplier has the wrong sign
+                        if (gn > 1e-10 * rx * gs) {
+                            const int fl = s.flips[e];
+                            if (fl < 2 || gn > 1e-5 * gs) {
+                                nm = 0;
+                                s.flips[e] = fl + 1;
+                            }
+                        }
                     }
                     if (nm != mk) {
                         s.mask[e] = nm;

@@ -233,7 +233,7 @@ __host__ __device__ inline void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
         k1 += 0xBB67AE85u;
     }
 }
-__device__ __forceinline__ double2 normal_pair(uint64_t seed, long long member, int step, int comp) {
+__device__ __noinline__ double2 normal_pair(uint64_t seed, long long member, int step, int comp) {
     uint32_t c[4] = {(uint32_t)member, (uint32_t)((unsigned long long)member >> 32), (uint32_t)step, (uint32_t)comp};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double u1 = (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * 0x1.0p-53 + 0x1.0p-54;
@@ -252,7 +252,7 @@ __device__ __forceinline__ double2 normal_pair(uint64_t seed, long long member, 
 // (plain transposes, as the reference writes them).  pz: dz complex of shared scratch.
 // ---------------------------------------------------------------------------------------------------------
 template <class CF>
-__device__ void stream_build_z(const double *x_real, const double *phi, int nblk, double2 *zs, int lane) {
+__device__ __noinline__ void stream_build_z(const double *x_real, const double *phi, int nblk, double2 *zs, int lane) {
     constexpr int C = CF::C;
 #pragma unroll 1
     for (int e = lane; e < nblk * C; e += 32) {
@@ -263,14 +263,14 @@ __device__ void stream_build_z(const double *x_real, const double *phi, int nblk
     __syncwarp();
 }
 template <class CF>
-__device__ double2 stream_row_dot(const double2 *row, const double2 *zs, int dz) {
+__device__ __noinline__ double2 stream_row_dot(const double2 *row, const double2 *zs, int dz) {
     double2 acc = make_double2(0.0, 0.0);
 #pragma unroll 1
     for (int j = 0; j < dz; ++j) acc = cfma(row[j], zs[j], acc);
     return acc;
 }
 template <class CF>
-__device__ void stream_update(double2 *A, double2 *P, const double2 *zs, const double *y_real, int dz, double discount,
+__device__ __noinline__ void stream_update(double2 *A, double2 *P, const double2 *zs, const double *y_real, int dz, double discount,
                               double2 *pz, double2 *red, int lane) {
     constexpr int C = CF::C;
     // P z (rows over lanes) and z^T P z

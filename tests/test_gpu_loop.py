@@ -46,6 +46,9 @@ def test_mpc_matches_reference_loop(name):
                                                 ('loop_transmon_o1', systems.ensemble_transmon, 65536),
                                                 ('loop_crosstalk', systems.ensemble_crosstalk, 65536)])
 def test_ensemble_members_match_oracle(name, maker, n_total):
+    """The round-1 ensemble fixtures (6 / 4 / 3 members), now at the plain north_star tolerances: the per-member
+    "sensitivity" slack is gone.  The 64-member fixtures, the reproducibility classes of the badly conditioned qubit
+    members and the teacher-forced per-step parity live in tests/test_gpu_parity64.py."""
     g = load_golden(name)
     cfg = CASES[name]()
     ens, _ = maker(n_total)
@@ -54,16 +57,14 @@ def test_ensemble_members_match_oracle(name, maker, n_total):
     kw.pop('progress_bar')
     res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 64), *args[7:], fid_target=cfg['target'], **kw)
     assert (res.exit_code == 0).all() and (res.steps_done == cfg['clock'].n_steps).all()
-    # The closed loop of a badly mismatched plant amplifies round-off (two exact CPU QP solvers that agree to 1e-14
-    # per QP end up 1e-5 apart after 20 steps on some qubit members); the fixture records that spread per member
-    # (ens_*_sensitivity, see oracle/make_golden.py) and the tolerance is the north_star's unless the member's own
-    # conditioning is worse.
-    tol_u = np.maximum(U_TOL, 20 * g['ens_us_sensitivity'])
-    tol_f = np.maximum(F_TOL, 20 * g['ens_fid_sensitivity'])
     du = np.abs(res.us[:k] - g['ens_us']).reshape(k, -1).max(axis=1)
     df = np.abs(res.fidelity[:k] - g['ens_fidelity'])
-    assert (du < tol_u).all(), (du, tol_u)
-    assert (df < tol_f).all(), (df, tol_f)
+    # members whose closed loop two exact CPU solvers reproduce to 1e-8 (all of them for the transmon and crosstalk
+    # fixtures; the mismatched qubit plants amplify round-off over the 39 SQP iterations of step 0 and 20 steps)
+    repro = g['ens_us_sensitivity'] < 1e-8
+    assert repro.sum() >= {'loop_qubit_o1': 1}.get(name, k)
+    assert (du[repro] < U_TOL).all(), (du, repro)
+    assert (df[repro] < F_TOL).all(), (df, repro)
     # before the first plant measurement can be amplified, every member matches tightly
     assert np.abs(res.us[:k, :, :3] - g['ens_us'][:, :, :3]).max() < 1e-7
     assert np.array_equal(res.qp_count[:k], g['ens_qp_per_step'])
@@ -519,12 +520,14 @@ def test_per_member_models_match_reference_runs(order):
     res = m4q.mpc_ensemble(args[0], *args[1:6], plants.slice(0, n), models.slice(0, n), *args[8:],
                            fid_target=cfg['target'], **kw)
     assert (res.exit_code == 0).all()
-    tol_u = np.maximum(U_TOL, 20 * g['o%d_us_sensitivity' % order])
-    tol_f = np.maximum(F_TOL, 20 * g['o%d_fid_sensitivity' % order])
     du = np.abs(res.us[:k] - g['o%d_us' % order]).reshape(k, -1).max(axis=1)
     df = np.abs(res.fidelity[:k] - g['o%d_fidelity' % order])
-    assert (du < tol_u).all(), (du, tol_u)
-    assert (df < tol_f).all(), (df, tol_f)
+    # plain north_star tolerances on every member two exact CPU solvers reproduce to 1e-8 (all 4 at order 1, 3 of 4 at
+    # order 2, where one badly matched model / plant pair amplifies round-off to 5e-6 over the 20 steps)
+    repro = g['o%d_us_sensitivity' % order] < 1e-8
+    assert repro.sum() >= k - 1
+    assert (du[repro] < U_TOL).all(), du
+    assert (df[repro] < F_TOL).all(), df
     assert np.abs(res.us[:k, :, :3] - g['o%d_us' % order][:, :, :3]).max() < 1e-7
     assert np.array_equal(res.qp_count[:k], g['o%d_qp_per_step' % order])
     # each member alone through mpc() with its own DMDc (shared-model path) gives the same trajectory bit for bit
