@@ -1725,7 +1725,11 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
             attr.accessPolicyWindow.num_bytes = ws_bytes < (size_t)max_window ? ws_bytes : (size_t)max_window;
             attr.accessPolicyWindow.hitRatio = reserved >= ws_bytes ? 1.0f : (float)reserved / (float)ws_bytes;
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            // the part of the window that does not get the persisting property: "normal" lets it compete for the rest of
+            // L2 (with 16 warps per SM the workspaces are 100 MB, more than the persisting carve-out), "streaming" would
+            // evict it first and re-read it from HBM on every sweep
+            const char *mp = getenv("M4Q_L2_MISS");
+            attr.accessPolicyWindow.missProp = (mp && mp[0] == 's') ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
             window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
         }
         cudaGetLastError();

@@ -117,24 +117,28 @@ def test_expm_large_ensembles_use_the_thread_per_member_kernel(maker, shared):
 @pytest.mark.parametrize('polish', [1, 0])
 def test_quad_program(qp_golden, tag, polish):
     """optimize.py:12-60 against the exact oracle solutions: controls within 1e-8 in the default tight (polished)
-    mode -- the mode every parity claim is made in (north_star: 1e-5) -- and within 1e-3 in the plain-ADMM mode, which
-    like OSQP stops on residuals (fixed rho, so it is slow on the weakly regularised transmon QP)."""
+    mode -- the mode every parity claim is made in (north_star: 1e-5).  The plain-ADMM mode (polish = 0) stops, like
+    OSQP, on residuals; with rho adapted from the residual ratio (m4q_qp_settings.adaptive_rho) it meets the
+    north_star's 1e-5 on the controls at eps = 1e-8 within 5,000 iterations (measured, tools/admm_mode_sweep.py:
+    1.2e-7 / 2.0e-6 / 3.0e-6 on the qubit / transmon / crosstalk QPs; at eps = 1e-5 and 500 iterations the weakly
+    regularised transmon and crosstalk QPs -- R ~ 4e-4 next to B^T P B ~ 1 -- are only 2e-3 / 1e-2 away: a residual of
+    1e-5 on these problems is not an error of 1e-5, for OSQP either)."""
     g = qp_golden
     n = g['%s_x_init' % tag].shape[0]
     H = g['%s_U' % tag].shape[2]
     Q_ls = [g['%s_Q' % tag]] * H + [g['%s_Qf' % tag]]
     R_ls = [g['%s_R' % tag]] * H
-    settings = m4q._lib.qp_settings(polish=polish, max_admm=50000 if not polish else 0, eps=1e-6 if not polish else 0)
+    settings = m4q._lib.qp_settings(polish=polish, max_admm=5000 if not polish else 0, eps=1e-8 if not polish else 0)
     for i in range(n):
         X, U, obj, info = optimize.quad_program(
             g['%s_x_init' % tag][i], g['%s_X_bm' % tag][i], g['%s_U_bm' % tag][i], Q_ls, R_ls,
             list(g['%s_A' % tag][i]), list(g['%s_B' % tag][i]), list(g['%s_D' % tag][i]), g['%s_u_prev' % tag][i],
             float(g['%s_sat' % tag]), float(g['%s_du' % tag]), settings=settings)
         assert info.status_code == 0
-        tol_u = 1e-8 if polish else 1e-3
+        tol_u = 1e-8 if polish else 1e-5
         assert np.abs(U - g['%s_U' % tag][i]).max() < tol_u, (tag, i, np.abs(U - g['%s_U' % tag][i]).max())
         assert np.abs(X - g['%s_X' % tag][i]).max() < 100 * tol_u
-        assert abs(obj - float(g['%s_obj' % tag][i])) < (1e-9 if polish else 1e-4) * max(1.0, abs(float(g['%s_obj' % tag][i])))
+        assert abs(obj - float(g['%s_obj' % tag][i])) < (1e-9 if polish else 1e-6) * max(1.0, abs(float(g['%s_obj' % tag][i])))
         sat, du = float(g['%s_sat' % tag]), float(g['%s_du' % tag])
         assert np.abs(U).max() <= sat + 1e-12
         assert np.abs(U[:, 0] - g['%s_u_prev' % tag][i]).max() <= du + 1e-12
