@@ -37,7 +37,10 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int next_mod(int x, int r, int m) { return x + ((r - x % m) % m + m) % m; }
 __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
-template <int C_, int M_> struct Tiles { static constexpr int MAXW = 16; };   // 128 registers
+#ifndef M4Q_MAXW_4
+#define M4Q_MAXW_4 32
+#endif
+template <int C_, int M_> struct Tiles { static constexpr int MAXW = C_ == 4 ? M4Q_MAXW_4 : 16; };   // C = 4: 32 warps x 64 registers (+18 % on the qubit, spills and all); else 16 x 128
 #ifndef M4Q_MAXW_92
 #define M4Q_MAXW_92 16
 #endif
