@@ -781,6 +781,8 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
                                              bool masked, int lane) {
     constexpr int C = CF::C, N = CF::N, M = CF::M, Q = CF::Q;
     constexpr int NT = CF::NT, GT = CF::GT, TT = CF::TT, KR = CF::KR, LDP = CF::LDP2, LDG = CF::LDG2;
+    constexpr bool LASTNAT = (N % 8 != 0) && (N % 8 <= 4);   // ragged last contraction tile: one k-step of 4 indices
+    constexpr int KSTEPS = 2 * NT - (LASTNAT ? 1 : 0);
     using R_ = Rec<CF>;
     const Slab<CF> s = slab_view<CF>(sr);
     const StageOps ops = localize<FUSED>(ops_in);
@@ -795,6 +797,15 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
     }
 #pragma unroll 1
     for (int e = lane; e < KR * LDG; e += 32) s.AB[e] = 0.0;
+    // where the entries of A_t this lane forms go: element e = lane + 32 q of the row-major C x C block
+    constexpr int NE = cdiv(C * C, 32);
+    int g_off[NE], r_off[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) {
+        const int e = lane + 32 * q, r = e / C, j = e % C;
+        g_off[q] = e < C * C ? r * LDG + j : -1;
+        r_off[q] = r * R_::CA + j;
+    }
     constexpr int BD = R_::SMALL - R_::B;   // [B_t | D_t]
     prefetch_block<BD>(s.ring + ((H - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
@@ -808,7 +819,6 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
         if (t > 0) prefetch_block<BD>(s.ring + ((t - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, t - 1) + R_::B, lane);
         // realified A_t = sum_k phi_k block_k into G[:, 0:N] (and, complex, into the record for the vector sweeps)
         {
-            constexpr int NE = cdiv(C * C, 32);
             double ar[NE], ai[NE];
 #pragma unroll
             for (int q = 0; q < NE; ++q) ar[q] = ai[q] = 0.0;
@@ -828,14 +838,13 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
             }
 #pragma unroll
             for (int q = 0; q < NE; ++q) {
-                const int e = lane + 32 * q;
-                if (e < C * C) {
-                    const int r = e / C, j = e % C;
-                    s.AB[r * LDG + j] = ar[q];
-                    s.AB[r * LDG + C + j] = -ai[q];
-                    s.AB[(C + r) * LDG + j] = ai[q];
-                    s.AB[(C + r) * LDG + C + j] = ar[q];
-                    reinterpret_cast<double2 *>(rec + R_::AT)[r * R_::CA + j] = make_double2(ar[q], ai[q]);
+                if (g_off[q] >= 0) {
+                    double *g = s.AB + g_off[q];
+                    g[0] = ar[q];
+                    g[C] = -ai[q];
+                    g[C * LDG] = ai[q];
+                    g[C * LDG + C] = ar[q];
+                    reinterpret_cast<double2 *>(rec + R_::AT)[r_off[q]] = make_double2(ar[q], ai[q]);
                 }
             }
         }
@@ -861,9 +870,11 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
 #pragma unroll
             for (int mi = 0; mi < NT; ++mi) w[qi][mi][0] = w[qi][mi][1] = 0.0;
         {
-            // operand rows of k-step (kt, e): 8 kt + 2 c4 + e, padding indices of the last tile -> the zero row N
+            // operand rows of k-step ks: tile kt = ks / 2, e = ks % 2 -> 8 kt + 2 c4 + e; when the last tile holds at most 4
+            // real indices (N = 18: two) it is ONE step over 8 kt + c4 instead, padding indices -> the zero row
             auto row_of = [&](int ks) {
-                const int r = (ks >> 1) * 8 + 2 * c4 + (ks & 1);
+                int r = (ks >> 1) * 8 + 2 * c4 + (ks & 1);
+                if (LASTNAT && ks == KSTEPS - 1) r = (NT - 1) * 8 + c4;
                 return r < N ? r : KR - 1;
             };
             const double *gb0 = s.AB + g8, *pb0 = s.P + g8;
@@ -876,9 +887,9 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
                 for (int mi = 0; mi < NT; ++mi) pf[mi] = pb0[r * LDP + mi * 8];
             }
 #pragma unroll 1
-            for (int ks = 0; ks < 2 * NT; ++ks) {
+            for (int ks = 0; ks < KSTEPS; ++ks) {
                 // next step's fragments in flight while this step's MMAs issue; the last step reloads its own
-                const int r = row_of(ks + 1 < 2 * NT ? ks + 1 : ks);
+                const int r = row_of(ks + 1 < KSTEPS ? ks + 1 : ks);
                 double gn[GT], pn[NT];
 #pragma unroll
                 for (int qi = 0; qi < GT; ++qi) gn[qi] = gb0[r * LDG + qi * 8];
@@ -914,15 +925,27 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
             for (int kt = 0; kt < NT; ++kt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
+                    if (LASTNAT && kt == NT - 1 && e == 1) continue;
                     int r = kt * 8 + 2 * c4 + e;
+                    if (LASTNAT && kt == NT - 1) r = kt * 8 + c4;
                     if (kt == NT - 1 && N % 8 != 0) r = r < N ? r : KR - 1;
                     double gb[TT];
 #pragma unroll
                     for (int ni = 0; ni < TT; ++ni) gb[ni] = gb0[r * LDG + ni * 8];
 #pragma unroll
-                    for (int qi = 0; qi < TT; ++qi)
+                    for (int qi = 0; qi < TT; ++qi) {
+                        double a = w[qi][kt][e];
+                        if (LASTNAT && kt == NT - 1) {
+                            // natural step of the last tile: index 8 kt + c4 is held by lane (g8, c4 / 2) in element c4 % 2
+                            // (in the first product that tile was accumulated in the natural order too, so element e of
+                            // lane c4' holds column 8 kt + 2 c4' + e as everywhere else)
+                            const int src = (lane & ~3) | (c4 >> 1);
+                            const double a0 = __shfl_sync(FULL, w[qi][kt][0], src), a1 = __shfl_sync(FULL, w[qi][kt][1], src);
+                            a = (c4 & 1) ? a1 : a0;
+                        }
 #pragma unroll
-                        for (int ni = qi; ni < TT; ++ni) dmma(tt[qi][ni], w[qi][kt][e], gb[ni]);
+                        for (int ni = qi; ni < TT; ++ni) dmma(tt[qi][ni], a, gb[ni]);
+                    }
                 }
         }
         // ---- publish the control columns: T12[i][a] (i < N) -> T21[a][i], T22 -> S (upper part, mirrored)
