@@ -905,6 +905,8 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         int status = qp_solve<CF, false>(sr, ops, qp, a.set, lane, cnt);
         const double obj = qp_objective<CF>(sr, qp, lane);
         if (!isfinite(obj)) status = 3;   // mpc.py:200
+        // empty stage-0 box (u_prev further than du outside the saturation range): infeasible, as the reference's solver says
+        if (__any_sync(FULL, lane < M && s.lo0[lane < M ? lane : 0] > s.hi0[lane < M ? lane : 0])) status = 3;
         double2 *Xo = a.X_out + (size_t)k * C * (H + 1);
         double *Uo = a.U_out + (size_t)k * M * H;
         const double *wXo = ws_Xo<CF>(sr);

@@ -88,6 +88,14 @@ def expm_segments(x0, H0, H1, u_seg, dt, shared=False, return_propagators=False)
     n_seg, m = u.shape[1], u.shape[2]
     H0d = _lib.dev(H0, np.complex128)
     H1d = _lib.dev(H1, np.complex128)
+    if d * d != dd or H0d.shape[-1] != d or H0d.shape[-2] != d:
+        raise ValueError('x0 has %d entries per member, H0 is %s: the plant state is vec(rho) of a d x d matrix'
+                         % (dd, tuple(H0d.shape)))
+    if H1d.shape[-3] != m or H1d.shape[-1] != d:
+        raise IndexError('u_seg has %d controls per segment, H1 is %s (one drive Hamiltonian per control)'
+                         % (m, tuple(H1d.shape)))
+    if u.shape[0] != n or (not shared and (H0d.shape[0] != n or H1d.shape[0] != n)):
+        raise ValueError('batch sizes differ: x0 %d, u_seg %d, H0 %s, H1 %s' % (n, u.shape[0], tuple(H0d.shape), tuple(H1d.shape)))
     out = _lib.empty((n, n_seg, dd), np.complex128)
     props = _lib.empty((n, n_seg, d, d), np.complex128) if return_propagators else None
     _lib.check(lib.m4q_expm_step_batched(n, d, m, n_seg, float(dt), _lib.ptr(H0d), _lib.ptr(H1d), int(shared),

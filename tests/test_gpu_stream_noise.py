@@ -200,3 +200,37 @@ def test_fidelity_convention():
                          fidelity_convention='sqrt', **kw)
     assert np.abs(b.fidelity - np.sqrt(a.fidelity)).max() < 1e-15        # qutip.fidelity = sqrt(<psi|rho|psi>)
     assert np.array_equal(a.us, b.us)
+
+
+def test_argument_checks_zeroed_tails_and_the_empty_rate_box():
+    """shape mismatches raise instead of reading out of bounds; members that stop early leave zeros (not
+    uninitialised memory) beyond steps_done; a stage-0 box emptied by the rate bound is exit code 3 (the reference's
+    solver reports the problem infeasible, mpc.py:200-203)."""
+    from mpc4quantum_b200.mpc import ClosedLoopPlan
+    from mpc4quantum_b200 import _lib
+    from mpc4quantum_b200.experiment import expm_segments
+    cfg = systems.config_transmon(1, horizon=8, n_steps=6)
+    ens, _ = systems.ensemble_transmon(4096)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    with pytest.raises(ValueError, match='dim_u'):           # a one-control ensemble for a two-control problem
+        m4q.mpc_ensemble(args[0], *args[1:6], m4q.EnsembleQExperiment(ens.H0[:4], ens.H1[:4, :1]), *args[7:], **kw)
+    with pytest.raises(ValueError, match='plant state'):
+        m4q.mpc_ensemble(args[0][:4], *args[1:6], ens.slice(0, 4), *args[7:], **kw)
+    with pytest.raises(IndexError, match='drive Hamiltonian'):
+        bad = m4q.QExperiment(cfg['experiment'].H0, cfg['experiment'].H1_list[:1])
+        m4q.mpc(args[0], *args[1:6], bad, *args[7:], **kw)
+    with pytest.raises(IndexError, match='controls per segment'):
+        expm_segments(np.zeros((2, 9), complex), ens.H0[:2], ens.H1[:2], np.zeros((2, 3, 1)), 0.25)
+    # early exit: infidelity threshold met at once -> exit code 1 after one step, zeros beyond
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 8), *args[7:], fid_target=cfg['target'],
+                           exit_infidelity=2.0, **kw)
+    assert (res.exit_code == 1).all() and (res.steps_done == 1).all()
+    assert np.abs(res.us[:, :, 1:]).max() == 0 and np.abs(res.xs[:, :, 2:]).max() == 0 and (res.qp_count[:, 1:] == 0).all()
+    # empty rate box: reference control of step 0 far outside [-sat, sat] with a tight du
+    cfg2 = systems.config_transmon(1, horizon=8, n_steps=6)
+    U_targ = cfg2['U_targ'].copy()
+    U_targ[:, 0] = 10 * cfg2['sat']
+    res = m4q.mpc_ensemble(cfg2['x0'], cfg2['dim_u'], cfg2['order'], cfg2['X_targ'], U_targ, cfg2['clock'], ens.slice(0, 8),
+                           cfg2['model'], cfg2['Q'], cfg2['R'], cfg2['Qf'], sat=cfg2['sat'], du=0.1, fid_target=cfg2['target'])
+    assert (res.exit_code == 3).all() and (res.steps_done == 0).all()

@@ -255,3 +255,28 @@ def test_model_containers_for_ensembles_and_exact_mode():
     p = gate['x0']
     pf = gate['X_targ'][:, 0]
     assert abs(np.vdot(p - pf, p - pf).real - 8 * (1 - np.real(np.vdot(gate['target'], p)))) < 1e-12
+
+
+def test_shard_draws_equal_slices_of_the_full_draw():
+    """Every rank draws only its block of the seeded ensemble (PCG64.advance): bit-identical to slicing the full draw, for
+    every ensemble and for ragged shard bounds."""
+    from mpc4quantum_b200.ensemble import shard_bounds
+    n_total, world = 1001, 3
+    for maker in (systems.ensemble_qubit, systems.ensemble_transmon, systems.ensemble_crosstalk, systems.ensemble_not_gate):
+        full, params = maker(n_total)
+        seen = 0
+        for rank in range(world):
+            lo, hi = shard_bounds(n_total, rank, world)
+            part, pp = maker(n_total, lo=lo, hi=hi)
+            assert np.array_equal(part.H0, full.H0[lo:hi]) and np.array_equal(part.H1, full.H1[lo:hi])
+            for k in params:
+                assert np.array_equal(pp[k], params[k][lo:hi])
+            seen += len(part)
+        assert seen == n_total
+    L, _ = systems.transmon_model_liouvillians(257)
+    L2, _ = systems.transmon_model_liouvillians(257, lo=250, hi=257)
+    assert np.array_equal(L[250:], L2)
+    # the legacy stream: what np.random.default_rng(seed).uniform(.., N) gave before sharding existed
+    rng = np.random.default_rng(systems.ENSEMBLE_SEED)
+    k = rng.uniform(0.9, 1.1, 64)
+    assert np.array_equal(systems.ensemble_transmon(64)[1]['anharm_scale'], k)
