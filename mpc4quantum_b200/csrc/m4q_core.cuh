@@ -114,7 +114,7 @@ template <class CF> __host__ __device__ constexpr int ws_doubles(int H) {
 }
 
 template <class CF> struct Slab {
-    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *phi, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr, *mbar;
+    double *P, *AB, *W, *T21, *S, *ring, *kk, *hl, *Ug, *Uo, *z, *y, *x0, *va, *vb, *xT, *lo0, *hi0, *xcur, *xmeas, *scr, *mbar;
     double *recring;   // 2-slot ring of whole stage records for the vector sweeps (aliases the factor scratch)
     double *xd;        // 2 N doubles of scratch for the general-cost adjoint sweep
     int *mask;
@@ -159,7 +159,6 @@ template <class CF> struct Slab {
         take(&q->ring, 2 * Rec<CF>::BDSLOT, 16);   // factor: [B_t | D_t] of two stages
         take(&q->kk, H * M);
         take(&q->hl, H * M);
-        take(&q->phi, H * nblk);
         take(&q->Ug, H * M);
         take(&q->Uo, H * M);
         take(&q->z, H * M);
@@ -283,11 +282,33 @@ struct StageOps {
     int stage_stride;        // in complex elements; 0 for the fused model
     int soff;                // FUSED: offset (doubles) of the blocks in dynamic shared memory
     int soffT;               // FUSED, c multiple of 8: offset of the transposed copies of blocks 1..p (0: none)
+    // block weights of a stage: w_0 = 1, w_k = the k-th monomial of the stage's guess control (linearize.py:123-128),
+    // evaluated where they are needed from the exponent table instead of being stored per stage (H (p + 1) doubles of
+    // shared memory per member, 4.8 KB at H = 100 with the order-2 library).  pow == nullptr: dense stage operators, w = 1.
+    const int *pow;          // [p][M] exponents (FUSED: re-derived from pow_soff)
+    int pow_soff;            // FUSED: offset (doubles) of the exponent table in dynamic shared memory
+    int first_order;         // the library is (u_1, .., u_M): w_k = u_{k-1}
 };
+template <int M> __device__ __forceinline__ double stage_weight(const StageOps &o, const double *u, int kb) {
+    if (kb == 0 || o.pow == nullptr) return 1.0;
+    if (o.first_order) return u[kb - 1];
+    double ph = 1.0;
+#pragma unroll
+    for (int l = 0; l < M; ++l) {
+        const int e = o.pow[(kb - 1) * M + l];
+        const double ul = u[l];
+#pragma unroll 1
+        for (int q = 0; q < e; ++q) ph *= ul;
+    }
+    return ph;
+}
 // FUSED = true: model blocks and cost matrices live in dynamic shared memory at known offsets
 template <bool FUSED> __device__ __forceinline__ StageOps localize(const StageOps &o) {
     StageOps r = o;
-    if (FUSED) r.blocks = reinterpret_cast<const double2 *>(dyn_smem() + o.soff);
+    if (FUSED) {
+        r.blocks = reinterpret_cast<const double2 *>(dyn_smem() + o.soff);
+        r.pow = reinterpret_cast<const int *>(dyn_smem() + o.pow_soff);
+    }
     return r;
 }
 
@@ -544,7 +565,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
     prefetch_block<BD>(s.ring + ((H - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *phi_t = s.phi + t * ops.nblk;
+        const double *ug_t = s.Ug + t * M;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
         const double *Bt = s.ring + (t & 1) * R_::BDSLOT, *Dt = Bt + (R_::D - R_::B);
         double *rec = ws_rec<CF>(sr, t);
@@ -562,7 +583,7 @@ __device__ __noinline__ void riccati_factor(SlabRef sr, const StageOps &ops_in, 
             const int qlast = (C * C - 1 - lane) >> 5;   // last valid q of this lane
 #pragma unroll 1
             for (int kb = 0; kb < ops.nblk; ++kb, bp += C * C) {
-                const double ph = phi_t[kb];
+                const double ph = stage_weight<M>(ops, ug_t, kb);
                 double2 v[NE];
 #pragma unroll
                 for (int q = 0; q < NE; ++q) v[q] = bp[32 * (q < qlast ? q : qlast)];
@@ -810,7 +831,7 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
     prefetch_block<BD>(s.ring + ((H - 1) & 1) * R_::BDSLOT, ws_rec<CF>(sr, H - 1) + R_::B, lane);
 #pragma unroll 1
     for (int t = H - 1; t >= 0; --t) {
-        const double *phi_t = s.phi + t * ops.nblk;
+        const double *ug_t = s.Ug + t * M;
         const double2 *blk0 = ops.blocks + (size_t)t * ops.stage_stride;
         const double *Bt = s.ring + (t & 1) * R_::BDSLOT, *Dt = Bt + (R_::D - R_::B);
         double *rec = ws_rec<CF>(sr, t);
@@ -826,7 +847,7 @@ __device__ __noinline__ void riccati_factor2(SlabRef sr, const StageOps &ops_in,
             const int qlast = (C * C - 1 - lane) >> 5;   // last valid q of this lane (loads clamped, not predicated)
 #pragma unroll 1
             for (int kb = 0; kb < ops.nblk; ++kb, bp += C * C) {
-                const double ph = phi_t[kb];
+                const double ph = stage_weight<M>(ops, ug_t, kb);
                 double2 v[NE];
 #pragma unroll
                 for (int q = 0; q < NE; ++q) v[q] = bp[32 * (q < qlast ? q : qlast)];
@@ -1497,7 +1518,9 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 const double *rec = ws_rec<CF>(sr, t);
                 if (lane < N) s.va[lane] = x;
                 __syncwarp();
-                const double ax = apply_A<CF>(ops, s.phi + t * ops.nblk, t, s.va, lane);
+                if (lane < ops.nblk) s.xd[lane] = stage_weight<M>(ops, s.Ug + t * M, lane);
+                __syncwarp();
+                const double ax = apply_A<CF>(ops, s.xd, t, s.va, lane);
                 if (lane < N) {
                     double xn = ax + rec[Rec<CF>::D + lane];
 #pragma unroll
@@ -1704,11 +1727,9 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
             vec[lane] = x_n;
             if (t + 1 < H) x_n = Xg[(t + 1) * N + lane];
         }
-        // monomials and derivative weights: lane k < p computes its own
-        if (first_order) {
-            if (lane < M) s.phi[t * model.nblk + 1 + lane] = s.Ug[t * M + lane];
-        } else if (lane < p) {
-            double phi = 1.0;
+        // derivative weights of the monomials: lane k < p computes its own (the monomials themselves are evaluated where
+        // they are used, stage_weight())
+        if (!first_order && lane < p) {
             double dw[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) dw[i] = (double)pow[lane * M + i];
@@ -1722,15 +1743,12 @@ __device__ __noinline__ void linearize(SlabRef sr, const StageOps &model_in, con
                     pwm1 = pw;
                     pw *= ul;
                 }
-                phi *= pw;
 #pragma unroll
                 for (int i = 0; i < M; ++i) dw[i] *= (i == l) ? (e > 0 ? pwm1 : 0.0) : pw;
             }
-            s.phi[t * model.nblk + 1 + lane] = phi;
 #pragma unroll
             for (int i = 0; i < M; ++i) dco[lane * M + i] = dw[i];
         }
-        if (lane == 31) s.phi[t * model.nblk] = 1.0;
         __syncwarp();
         if (act) {
             const double *xp = vec + (im ? C : 0), *xq = vec + (im ? 0 : C);

@@ -362,7 +362,6 @@ __device__ __noinline__ void linearize_exact(SlabRef sr, const double2 *gen, dou
 #pragma unroll 1
     for (int t = 0; t < sr.H; ++t) {
         if (lane < C) xs[lane] = make_double2(Xg[t * N + lane], Xg[t * N + C + lane]);
-        if (lane == 0) s.phi[t] = 1.0;
         __syncwarp();
         exact_stage<CF>(gen, s.Ug + t * M, xs, dt, scr, lane);
         const double2 *T = scr + CC, *b = scr + exact_b_offset<CF>();
@@ -440,6 +439,14 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
     model.stage_stride = 0;
     model.soff = 0;
     model.soffT = (C % 8 == 0 && !a.model_per_member) ? soffT : 0;
+    model.pow = pow;
+    model.pow_soff = (int)(reinterpret_cast<double *>(pow) - smem);
+    {
+        bool fo = a.nblk - 1 == M;
+        if (fo)
+            for (int e = 0; e < M * M; ++e) fo &= pow[e] == ((e / M == e % M) ? 1 : 0);
+        model.first_order = fo;
+    }
     if (a.model_per_member) {
         // perturbed MODELS: the member's own blocks sit behind its slab (the slab stride includes them)
         model.soff = sr.off + a.slab_doubles - 2 * a.nblk * C * C;
@@ -568,6 +575,9 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                         dense.stage_stride = C * C;
                         dense.soff = 0;
                         dense.soffT = 0;
+                        dense.pow = nullptr;
+                        dense.pow_soff = 0;
+                        dense.first_order = 0;
                         status = qp_solve<CF, false>(sr, dense, qp, a.set, lane, cnt);
                     } else {
                         linearize<CF, true>(sr, model, pow, lane);                  // mpc.py:175
@@ -858,8 +868,6 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
             ws_rec<CF>(sr, t)[Rec<CF>::D + kk] = kk < C ? v.x : v.y;
         }
 #pragma unroll 1
-        for (int e = lane; e < H; e += 32) s.phi[e] = 1.0;
-#pragma unroll 1
         for (int e = lane; e < H * M; e += 32) {
             s.z[e] = 0.0;
             s.y[e] = 0.0;
@@ -887,6 +895,9 @@ __global__ void __launch_bounds__(CF::MAXW * 32) qp_kernel(const QpArgs a) {
         ops.stage_stride = C * C;
         ops.soff = 0;
         ops.soffT = 0;
+        ops.pow = nullptr;
+        ops.pow_soff = 0;
+        ops.first_order = 0;
         QPData qp;
         qp.Q = wQ;
         qp.q_stride = N * N;
