@@ -49,7 +49,14 @@ typedef struct {
                             1: always run an ADMM block to eps before the active-set rounds */
     int32_t adaptive_rho;/* 0 / 1: rho is rescaled from the primal / dual residual ratio at a few check points, with a
                             re-factorisation, as OSQP's adaptive_rho does (default); -1: fixed rho */
-    int32_t reserved_;   /* keeps the struct a multiple of 8 bytes; must be 0 */
+    int32_t kkt_fallback;/* tight mode only.  0: a QP that the Riccati-based active set cannot certify ends with status 2
+                            (default).  1: such a QP is handed to a pivoted stage-wise KKT solve (states and costates as
+                            unknowns of one almost-block-diagonal system, row partial pivoting) with primal-dual active-set
+                            rounds from an empty working set -- what the reference's sparse solver does, and the only thing
+                            that works for the order-1 model at H = 100, where the cost-to-go leaves the fp64 range.
+                            2: the same as soon as the active-set rounds fail once, and from then on for every QP of that
+                            member.  Needs H (2n+m)(4n+2m+2) doubles per resident warp (n = 2c), which
+                            m4q_mpc_table_bytes / m4q_qp_workspace_bytes_kkt include when this is set. */
 } m4q_qp_settings;
 
 /* Problem description of the closed loop (mpc.py:128-304).  Shared (member-independent) data. */
@@ -168,6 +175,7 @@ int m4q_exact_linearize_batched(int64_t N, int32_t c, int32_t m, int32_t H, doub
  *   workspace: m4q_qp_workspace_bytes(N, c, m, H) bytes of device memory.
  */
 int64_t m4q_qp_workspace_bytes(int64_t N, int32_t c, int32_t m, int32_t H);
+int64_t m4q_qp_workspace_bytes_kkt(int64_t N, int32_t c, int32_t m, int32_t H);   /* with settings.kkt_fallback != 0 */
 int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H,
                         const double *x_init, const double *X_bm, const double *U_bm,
                         const double *Q_ls, const double *R_ls,

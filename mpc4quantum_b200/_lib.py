@@ -20,7 +20,7 @@ c_i32, c_i64, c_f64, c_vp = ct.c_int32, ct.c_int64, ct.c_double, ct.c_void_p
 class QPSettings(ct.Structure):
     """m4q_qp_settings (include/m4q.h)."""
     _fields_ = [('rho', c_f64), ('alpha', c_f64), ('eps', c_f64), ('max_admm', c_i32), ('polish', c_i32),
-                ('max_polish', c_i32), ('admm_first', c_i32), ('adaptive_rho', c_i32), ('reserved_', c_i32)]
+                ('max_polish', c_i32), ('admm_first', c_i32), ('adaptive_rho', c_i32), ('kkt_fallback', c_i32)]
 
 
 class MpcProblem(ct.Structure):
@@ -47,6 +47,7 @@ SIGNATURES = {
                                          c_vp]),
     'm4q_exact_linearize_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32, c_f64] + [c_vp] * 7),
     'm4q_qp_workspace_bytes': (c_i64, [c_i64, c_i32, c_i32, c_i32]),
+    'm4q_qp_workspace_bytes_kkt': (c_i64, [c_i64, c_i32, c_i32, c_i32]),
     'm4q_qp_admm_batched': (ct.c_int, [c_i64, c_i32, c_i32, c_i32] + [c_vp] * 9 + [c_f64, c_f64, c_i32,
                                        ct.POINTER(QPSettings)] + [c_vp] * 7),
     'm4q_line_search_workspace_bytes': (c_i64, [c_i32, c_i32, c_i32]),
@@ -137,6 +138,7 @@ def stream_ptr(stream=None):
     return c_vp(st.cuda_stream)
 
 
-def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0, admm_first=0, adaptive_rho=0):
+def qp_settings(rho=0.0, alpha=0.0, eps=0.0, max_admm=0, polish=1, max_polish=0, admm_first=0, adaptive_rho=0,
+                kkt_fallback=0):
     """Zeros select the library defaults (include/m4q.h)."""
-    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, admm_first, adaptive_rho, 0)
+    return QPSettings(rho, alpha, eps, max_admm, polish, max_polish, admm_first, adaptive_rho, kkt_fallback)

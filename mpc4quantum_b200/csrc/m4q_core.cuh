@@ -341,10 +341,14 @@ template <bool FUSED> __device__ __forceinline__ QPData localize(const QPData &q
 struct QPSet {
     double rho, alpha, eps;
     int max_admm, polish, max_polish, admm_first, adaptive_rho;
+    int kkt_mode;   // 0: off; 1: pivoted KKT solve as the last resort (where status 2 would be returned); 2: as soon as the
+                    // Riccati active-set rounds fail once, and from then on for every QP of the member (m4q_kkt.cuh)
+    double *kkt;    // this warp's KKT workspace (Kkt<CF>::doubles(H)), nullptr: none
 };
 
 struct Counters {
     int admm, factor, polish, solves;
+    int kkt;        // pivoted KKT solves (reported with the polish rounds)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1466,6 +1470,10 @@ __device__ __noinline__ void admm_block(SlabRef sr, const StageOps &ops_in, cons
             }
         }
 
+}   // namespace m4q
+#include "m4q_kkt.cuh"
+namespace m4q {
+
 // ---------------------------------------------------------------------------------------------------------
 // The QP (optimize.py:12-60).  Two building blocks share the Riccati kernels:
 //   * ADMM on the control box (u = z, z in [lo, hi]); u-update = equality-constrained LQ problem solved exactly by
@@ -1503,7 +1511,15 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     int status = 0;
     bool x_nonfinite = false;   // a non-finite state of the reported rollout (it propagates to x_H)
     bool run_admm = !set.polish || set.admm_first;
+    const bool kkt_ok = set.kkt != nullptr && set.kkt_mode > 0 && set.polish;
     for (;;) {
+        if (kkt_ok && set.kkt_mode >= 2 && cnt.kkt > 0) {
+            // an earlier QP of this member needed the pivoted KKT solve (cost-to-go beyond fp64: order-1 model at long
+            // horizons): go straight to it.  One factor call forms the stage operators A_t in the records.
+            factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, 0.0, false, lane);
+            status = kkt_active_set<CF, FUSED>(sr, qp_in, set, lane, cnt);
+            break;
+        }
         if (run_admm) admm_block<CF, FUSED>(sr, ops_in, qp_in, set, eps, lane, cnt);
         if (!set.polish) {
             // OSQP-equivalent mode: report the feasible iterate z and its rollout
@@ -1649,6 +1665,11 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         // not certified: (re)seed with an ADMM block at a tighter tolerance
         if (run_admm) eps *= 0.1;
         run_admm = true;
+        if (kkt_ok && (set.kkt_mode >= 2 || eps < 1e-10)) {
+            status = kkt_active_set<CF, FUSED>(sr, qp_in, set, lane, cnt);
+            x_nonfinite = false;
+            break;
+        }
         if (eps < 1e-10) {
             status = 2;   // could not certify: report the ADMM iterate (reference: solver warning -> exit code 2)
 #pragma unroll 1

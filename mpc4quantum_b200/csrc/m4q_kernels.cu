@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(CF::MAXW * 32) mpc_kernel(const MpcArgs a) {
                 if (a.step_begin == 0) c[0] = c[1] = c[2] = c[3] = 0;
                 c[0] += cnt.admm;
                 c[1] += cnt.factor;
-                c[2] += cnt.polish;
+                c[2] += cnt.polish + cnt.kkt;
                 c[3] += cnt.solves;
             }
         }
@@ -1683,6 +1683,8 @@ static QPSet qp_settings(const m4q_qp_settings *s) {
     q.max_polish = (s && s->max_polish > 0) ? s->max_polish : 8;
     q.admm_first = s ? s->admm_first : 0;
     q.adaptive_rho = (s && s->adaptive_rho < 0) ? 0 : 1;
+    q.kkt_mode = (s && s->kkt_fallback > 0 && q.polish) ? s->kkt_fallback : 0;
+    q.kkt = nullptr;   // set by the launchers when kkt_mode != 0
     return q;
 }
 
@@ -1747,6 +1749,10 @@ static int launch_mpc(const m4q_mpc_problem *p, long long n, const MpcArgs &base
         }
         cudaGetLastError();
     }
+    // the pivoted-KKT workspaces (one per resident warp, m4q_kkt.cuh) follow the other per-warp arrays
+    if (a.set.kkt_mode)
+        a.set.kkt = a.ws + (size_t)g.ctas * g.warps *
+                               (ws_doubles<CF>(p->horizon) + (p->model_mode == M4Q_MODEL_EXACT ? 2 * p->horizon * CF::C * CF::C : 0));
     if (p->model_mode == M4Q_MODEL_EXACT) {
         a.ws_exact = a.ws + (size_t)g.ctas * g.warps * ws_doubles<CF>(p->horizon);
         mpc_kernel<CF, true><<<g.ctas, g.warps * 32, g.smem, st>>>(a);
@@ -1947,6 +1953,23 @@ int64_t m4q_qp_workspace_bytes(int64_t N, int32_t c, int32_t m, int32_t H) {
     return (int64_t)sizeof(double) * N * per;
 }
 
+// with room for the pivoted-KKT workspaces of the resident warps (settings.kkt_fallback != 0)
+int64_t m4q_qp_workspace_bytes_kkt(int64_t N, int32_t c, int32_t m, int32_t H) {
+    const int64_t base = m4q_qp_workspace_bytes(N, c, m, H);
+    if (base < 0) return -1;
+    long long kkt = 0;
+    M4Q_DISPATCH(c, m, {
+        Geometry g;
+        const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
+        int count = 0;
+        const bool have_device = cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+        if (!have_device) cudaGetLastError();
+        if (plan(qp_kernel<CF>, CF::MAXW, slab, 0, 1LL << 40, have_device, &g) != 0) return -1;
+        kkt = (long long)g.ctas * g.warps * Kkt<CF>::doubles(H);
+    });
+    return base + (int64_t)sizeof(double) * kkt;
+}
+
 int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double *x_init, const double *X_bm,
                         const double *U_bm, const double *Q_ls, const double *R_ls, const double *A_ls, const double *B_ls,
                         const double *D_ls, const double *u_prev, double sat, double du, int32_t has_du,
@@ -1983,6 +2006,7 @@ int m4q_qp_admm_batched(int64_t N, int32_t c, int32_t m, int32_t H, const double
         const int slab = rup(Slab<CF>::doubles(H, 1, CF::C), 2);
         if (plan(qp_kernel<CF>, CF::MAXW, slab, 0, N, true, &g) != 0) return -1;
         a.slab_doubles = slab;
+        if (a.set.kkt_mode) a.set.kkt = a.ws + (size_t)N * qp_ws_doubles<CF>(H);   // sized by m4q_qp_workspace_bytes_kkt
         qp_kernel<CF><<<g.ctas, g.warps * 32, g.smem, (cudaStream_t)stream>>>(a);
     });
     M4Q_CUDA(cudaGetLastError());
@@ -2042,6 +2066,7 @@ int64_t m4q_mpc_table_bytes(const m4q_mpc_problem *p) {
         if (mpc_geometry<CF>(p, 1LL << 40, have_device, &g) != 0) return -1;
         ws = (long long)g.ctas * g.warps * ws_doubles<CF>(p->horizon);
         if (p->model_mode == M4Q_MODEL_EXACT) ws += (long long)g.ctas * g.warps * 2 * p->horizon * CF::C * CF::C;
+        if (p->qp.kkt_fallback > 0 && p->qp.polish) ws += (long long)g.ctas * g.warps * Kkt<CF>::doubles(p->horizon);
     });
     return (int64_t)sizeof(double) * (rup(TableLayout(2 * p->c, p->m, p->n_targ).total, 2) + ws);
 }

@@ -208,7 +208,11 @@ class ClosedLoopPlan:
             fid=None if fid_target is None else _lib.dev(np.asarray(fid_target, dtype=complex).reshape(-1),
                                                          np.complex128))
         kp = self._keep
-        st = settings if settings is not None else _lib.qp_settings()
+        # Default settings: long horizons get the pivoted KKT solve behind the Riccati path (include/m4q.h, kkt_fallback):
+        # as the last resort from H = 32, as the first resort after one failed certification beyond H = 64 (the order-1
+        # model at H = 100 leaves the fp64 range of the cost-to-go from the fourth step on)
+        st = settings if settings is not None else _lib.qp_settings(
+            kkt_fallback=2 if self.H > 64 else (1 if self.H >= 32 else 0))
         # external (host-stepped) plant: d = 0 tells the library that xs holds lifted model states
         self.prob = _lib.MpcProblem(
             self.c, self.m, self.p, 0 if self.external else self.d, self.H, self.S, int(clock.measure_freq),

@@ -51,8 +51,9 @@ def quad_program_batched(x_init, X_bm, U_bm, Q_ls, R_ls, A_ls, B_ls, Delta_ls, u
     obj = _lib.empty((n,), np.float64)
     status = _lib.empty((n,), np.int32)
     iters = _lib.empty((n, 2), np.int32)
-    ws = _lib.empty((int(lib.m4q_qp_workspace_bytes(n, c, m, H)),), np.uint8)
-    st = settings if settings is not None else _lib.qp_settings()
+    st = settings if settings is not None else _lib.qp_settings(kkt_fallback=2 if H > 64 else (1 if H >= 32 else 0))
+    ws_bytes = lib.m4q_qp_workspace_bytes_kkt if st.kkt_fallback else lib.m4q_qp_workspace_bytes
+    ws = _lib.empty((int(ws_bytes(n, c, m, H)),), np.uint8)
     _lib.check(lib.m4q_qp_admm_batched(n, c, m, H, _lib.ptr(xi), _lib.ptr(Xb), _lib.ptr(Ub), _lib.ptr(Q), _lib.ptr(R),
                                        _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.ptr(up), float(sat),
                                        float(du) if du is not None else 0.0, int(up is not None), st,

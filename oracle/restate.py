@@ -294,7 +294,7 @@ class _SparseQP:
             self._cache = (C2, lin, E, e)
         return self._cache
 
-    def solve_fixed(self, fixed, values):
+    def solve_fixed(self, fixed, values, want_grad=False):
         """Minimise with U[fixed] = values[fixed] and the rest free: one sparse KKT solve.
 
         KKT matrix [[2C, E^T, G^T], [E, 0, 0], [G, 0, 0]] with G the selector of the fixed controls.
@@ -316,7 +316,14 @@ class _SparseQP:
         U = sol[nx:nv].reshape(H, m).copy()
         U.reshape(-1)[fidx] = values.reshape(-1)[fidx]
         # states from the KKT solution itself (a rollout would amplify round-off by ||A||^H at long horizons)
-        return sol[:nx].reshape(H + 1, n).copy(), U
+        X = sol[:nx].reshape(H + 1, n).copy()
+        if not want_grad:
+            return X, U
+        # d cost / d U from the solve's own costates nu (the multipliers of E z = e; row block t+1 is the dynamics of
+        # stage t): 2 R (u - ub) - B^T nu_{t+1}.  Unlike gradient(), nothing is propagated through prod A_t.
+        nu = sol[nv:nv + nx].reshape(H + 1, n)
+        g = np.array([2 * self.R[t] @ (U[t] - self.ub[t]) - self.B[t].T @ nu[t + 1] for t in range(H)])
+        return X, U, g
 
 
 def _active_set(prob, lo, hi, max_rounds=40):
@@ -344,25 +351,68 @@ def _active_set(prob, lo, hi, max_rounds=40):
         seen.add(key)
         at_lo = (at_lo & ~rel_lo) | viol_lo
         at_hi = (at_hi & ~rel_hi) | viol_hi
-    return _primal_active_set(prob, lo, hi, np.clip(U, lo, hi))
+    try:
+        return _primal_active_set(prob, lo, hi, np.clip(U, lo, hi))
+    except RuntimeError:
+        return _active_set_kkt_multipliers(prob, lo, hi)
 
 
-def _primal_active_set(prob, lo, hi, U):
-    """Nocedal & Wright alg. 16.3 for the box: feasible iterates, one constraint added or dropped per round."""
+def _active_set_kkt_multipliers(prob, lo, hi, max_rounds=40):
+    """Last resort for the order-1 model at H = 100 (||prod A_t|| ~ 1e13): the adjoint gradient used above has a noise
+    floor of eps ||prod A_t||^2 and the multiplier signs cannot be read from it.  Same primal-dual rounds from the empty
+    working set, with the multipliers taken from the costates of the sparse KKT solve itself (a weakly active bound
+    that has been released twice stays pinned unless its multiplier is wrong beyond 1e-5 relative); if those do not
+    settle either (unconstrained optima ten box widths outside the box make the rounds erratic), the textbook primal
+    method, which cannot cycle, with the same multipliers."""
+    H, m = lo.shape
+    mask = np.zeros((H, m), dtype=int)
+    flips = np.zeros((H, m), dtype=int)
+    for _ in range(max_rounds):
+        fixed = mask != 0
+        vals = np.where(mask == 1, lo, np.where(mask == 2, hi, 0.0))
+        X, U, g = prob.solve_fixed(fixed, vals, want_grad=True)
+        gs = max(1.0, float(np.abs(g).max()))
+        viol_lo = ~fixed & (U < lo - 1e-12)
+        viol_hi = ~fixed & (U > hi + 1e-12)
+        gn = np.where(mask == 1, -g, np.where(mask == 2, g, 0.0))
+        rel = fixed & (gn > 1e-10 * gs) & ((flips < 2) | (gn > 1e-5 * gs))
+        if not (viol_lo.any() or viol_hi.any() or rel.any()):
+            return X, U, np.where(fixed, g, 0.0)
+        mask = mask.copy()
+        mask[viol_lo] = 1
+        mask[viol_hi] = 2
+        mask[rel] = 0
+        flips[rel] += 1
+    return _primal_active_set(prob, lo, hi, np.clip(np.zeros((H, m)), lo, hi), kkt_multipliers=True)
+
+
+def _primal_active_set(prob, lo, hi, U, kkt_multipliers=False):
+    """Nocedal & Wright alg. 16.3 for the box: feasible iterates, one constraint added per round.
+    kkt_multipliers: multipliers from the costates of the KKT solve instead of the adjoint gradient, and every
+    constraint with a wrong-signed multiplier dropped at once (the order-1 model at H = 100)."""
     H, m = lo.shape
     at_lo = U <= lo
     at_hi = (U >= hi) & ~at_lo
     for _ in range(20 * H * m + 100):
         fixed = at_lo | at_hi
         vals = np.where(at_lo, lo, np.where(at_hi, hi, 0.0))
-        Xe, Ue = prob.solve_fixed(fixed, vals)
+        if kkt_multipliers:
+            Xe, Ue, grad = prob.solve_fixed(fixed, vals, want_grad=True)
+        else:
+            Xe, Ue = prob.solve_fixed(fixed, vals)
         step = Ue - U
         if np.abs(step).max() <= 1e-11 * max(1.0, float(np.abs(U).max())):
-            grad = prob.gradient(Xe, Ue)
+            if not kkt_multipliers:
+                grad = prob.gradient(Xe, Ue)
             gs = max(1.0, float(np.abs(grad).max()))
             w = np.where(at_lo, -grad, np.where(at_hi, grad, 0.0))
             if w.max() <= 1e-9 * gs:
-                return Xe, Ue, grad
+                return Xe, Ue, (np.where(fixed, grad, 0.0) if kkt_multipliers else grad)
+            if kkt_multipliers:
+                drop = w > 1e-9 * gs
+                at_lo[drop] = False
+                at_hi[drop] = False
+                continue
             k = np.unravel_index(np.argmax(w), w.shape)
             at_lo[k] = False
             at_hi[k] = False

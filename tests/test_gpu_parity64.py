@@ -37,7 +37,7 @@ REPRO_TOL = 1e-8          # reference mpc() vs its numpy restatement: below this
 MIN_REPRODUCIBLE = {'qubit': 30, 'transmon': 64, 'crosstalk': 50}
 # order-1 model at H = 50: the QPs themselves are ill conditioned (cost-to-go entries ~1e10; two CPU runs of the reference
 # algorithm agree to 1e-6 over the closed loop): single steps are held to 1e-6, still 10x inside the north_star
-TF_TOL_BY_CONFIG = {'transmon_h50': 1e-6}
+TF_TOL_BY_CONFIG = {'transmon_h50': 1e-6, 'transmon_h100': 1e-6}
 
 CONFIGS = {
     'qubit': (lambda: systems.config_qubit(1), systems.ensemble_qubit, 4096),
@@ -47,7 +47,11 @@ CONFIGS = {
 # teacher forcing only: the order-1 model at H = 50 (cost-to-go entries ~1e10, every step from the third on needs the ADMM
 # re-seeding of the working set): 16 members x 20 steps
 TF_CONFIGS = dict(CONFIGS, transmon_h50=(lambda: systems.config_transmon(1, horizon=50, n_steps=20),
-                                         systems.ensemble_transmon, 65536))
+                                         systems.ensemble_transmon, 65536),
+                  # H = 100: ||prod A_t|| ~ 4e13, every QP from the fourth step on goes through the pivoted KKT solve
+                  # (csrc/m4q_kkt.cuh); 8 members x 20 steps
+                  transmon_h100=(lambda: systems.config_transmon(1, horizon=100, n_steps=20),
+                                 systems.ensemble_transmon, 65536))
 
 
 def _record(name, **vals):

@@ -6,6 +6,7 @@ import pytest
 import mpc4quantum_b200 as m4q
 from mpc4quantum_b200 import optimize, systems
 from mpc4quantum_b200.experiment import expm_segments
+from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -142,6 +143,40 @@ def test_quad_program(qp_golden, tag, polish):
         sat, du = float(g['%s_sat' % tag]), float(g['%s_du' % tag])
         assert np.abs(U).max() <= sat + 1e-12
         assert np.abs(U[:, 0] - g['%s_u_prev' % tag][i]).max() <= du + 1e-12
+
+
+def test_quad_program_h100_order1_pivoted_kkt():
+    """QPs of the reference loop at H = 100 with the order-1 model (steps 3, 4, 5, 9: ||prod A_t|| = 1e10 .. 4e13,
+    oracle/make_golden_h100.py).  The Riccati path cannot certify them; the pivoted stage-wise KKT solve
+    (csrc/m4q_kkt.cuh) must: status 0, controls within 1e-6 of the oracle's sparse solve (itself good to ~1e-8 on the
+    worst of them: tools/analysis/abd_full.py compares both with an 80-bit elimination)."""
+    g = load_golden('qp_h100')
+    n, H = g['h100_U'].shape[0], g['h100_U'].shape[2]
+    assert H == 100
+    Q_ls = [g['h100_Q']] * H + [g['h100_Qf']]
+    R_ls = [g['h100_R']] * H
+    sat, du = float(g['h100_sat']), float(g['h100_du'])
+    for i in range(n):
+        X, U, obj, info = optimize.quad_program(
+            g['h100_x_init'][i], g['h100_X_bm'][i], g['h100_U_bm'][i], Q_ls, R_ls, list(g['h100_A'][i]),
+            list(g['h100_B'][i]), list(g['h100_D'][i]), g['h100_u_prev'][i], sat, du)
+        assert info.status_code == 0, (i, info.status_code)
+        err = np.abs(U - g['h100_U'][i]).max()
+        assert err < 1e-6, (i, int(g['h100_step'][i]), err)
+        assert np.abs(X - g['h100_X'][i]).max() < 1e-6 * max(1.0, np.abs(g['h100_X'][i]).max())
+        assert np.abs(U).max() <= sat + 1e-12
+        assert np.abs(U[:, 0] - g['h100_u_prev'][i]).max() <= du + 1e-12
+    # without the fallback the same problems end with the solver warning (status 2), never with silent garbage
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        X, U, obj, info = optimize.quad_program(
+            g['h100_x_init'][0], g['h100_X_bm'][0], g['h100_U_bm'][0], Q_ls, R_ls, list(g['h100_A'][0]),
+            list(g['h100_B'][0]), list(g['h100_D'][0]), g['h100_u_prev'][0], sat, du,
+            settings=m4q._lib.qp_settings(kkt_fallback=0))
+    assert info.status_code in (0, 2)
+    if info.status_code == 0:
+        assert np.abs(U - g['h100_U'][0]).max() < 1e-5
 
 
 def test_quad_program_batched_matches_single(qp_golden):
