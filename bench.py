@@ -220,7 +220,7 @@ class Runner:
                       cfg['Qf'], cfg['sat'], cfg['du'])
         self.plan = m4q.ClosedLoopPlan(*self.margs, d=self.ens.d, lift_mode=self.ens.lift_mode,
                                        warm_start=cfg['warm_start'], fid_target=cfg['target'], capacity=self.n,
-                                       settings=_lib.qp_settings(admm_first=int(admm_first)))
+                                       settings=_lib.qp_settings(admm_first=int(admm_first)) if admm_first else None)
         self.geom = self.plan.launch_info(self.n)
         x0_plant = cfg['u0'] if cfg.get('kind') == 'process' else cfg['x0']     # gate synthesis: the propagator itself
         self.x0_host = np.ascontiguousarray(x0_plant.reshape(-1))
@@ -474,7 +474,9 @@ def main():
         if args.workload == 'transmon_h16':
             wl = {}
             todo = [('qubit', 4096, 'BASELINE config 2'), ('crosstalk', 65536, 'BASELINE config 4')] + \
-                   [('transmon_h%d' % h, 16384, 'BASELINE config 3 horizon sweep, order-1 model') for h in (10, 20, 50, 100)] + \
+                   [('transmon_h%d' % h, 16384, 'BASELINE config 3 horizon sweep, order-1 model') for h in (10, 20, 50)] + \
+                   [('transmon_h100', 4736, 'BASELINE config 3 horizon sweep, order-1 model: from the fourth step on every QP '
+                                            'goes through the pivoted KKT solve (interior point + polish)')] + \
                    [('transmon_o2_h100', 16384, 'config 3 horizon sweep, order-2 model')]
             if world == 8:
                 todo.append(('transmon_h16', 1 << 20, 'BASELINE config 5: 1 M perturbed transmons on 8 GPUs, '

@@ -17,13 +17,18 @@
 // accuracy of the solve (1e-7 at worst on the captured H = 100 problems, tools/analysis/abd_full.py) instead of the
 // noise of an adjoint sweep through the unstable dynamics.
 //
-// Active set: primal-dual rounds from an EMPTY working set, the iteration the oracle uses (oracle/restate.py:
-// _active_set); on the captured problems it settles in 1..25 rounds where the warm-started rounds cycle
-// (tools/analysis/abd_active.py).  Weakly active bounds get the same hysteresis as in qp_solve.
+// Working set: a primal-dual interior-point method whose every iteration is one such solve (kkt_active_set below).
 //
 // One warp per member as everywhere else; the elimination window (3N + M rows) lives in the same per-warp global
 // array and is served by L1/L2.  This path is cold for every configuration that the Riccati path certifies.
 #pragma once
+
+#ifndef M4Q_IPM_ITERS
+#define M4Q_IPM_ITERS 80
+#endif
+#ifndef M4Q_KKT_POLISH
+#define M4Q_KKT_POLISH 16
+#endif
 
 namespace m4q {
 
@@ -36,7 +41,10 @@ template <class CF> struct Kkt {
     static constexpr int CH = cdiv(LD, 32);    // column chunks of a row per lane
     static constexpr int CR = cdiv(ROWS, 32);  // rows of a column per lane
     static constexpr int CW = cdiv(W, 32);     // unknowns of a block per lane
-    __host__ __device__ static constexpr long long doubles(int H) { return (long long)(ROWS + (long long)H * W) * LD; }
+    // window | pivot rows of every block | the last solution [H + 2][W] (iterative refinement)
+    __host__ __device__ static constexpr long long doubles(int H) {
+        return (long long)(ROWS + (long long)H * W) * LD + (long long)(H + 2) * W;
+    }
 };
 
 // realified entry (k, j) of a complex C x C block stored with row stride CA: [[Re, -Im], [Im, Re]]
@@ -46,11 +54,17 @@ template <class CF> __device__ __forceinline__ double realified(const double2 *A
     return ((k < C) == (j < C)) ? a.x : (k >= C ? a.y : -a.y);
 }
 
-// One equality-constrained solve for the working set in slab.mask.  Out: Uo (slab), Xo (workspace), the gradient of the
-// objective w.r.t. every control in slab.kk (= the multipliers on pinned controls, ~0 on free ones).
+// One solve of the KKT system.  Out: Uo (slab), Xo (workspace), the gradient of the objective w.r.t. every control in
+// slab.kk (= the multipliers on pinned controls, ~0 on free ones).
+//   sigmu < 0:  working-set mode: controls with slab.mask != 0 are pinned to their bound.
+//               refine: the right-hand side is the residual of the previous solution (kept in the workspace) and the
+//               result is added to it -- one step of iterative refinement, a second elimination with the same pivots.
+//   sigmu >= 0: interior-point mode: every control is free and carries the barrier terms of the iterate
+//               (u, z_lo, z_hi) = (slab.z, slab.y, slab.hl):  (2 R + Sigma) u+ + B^T lam = 2 R ub + Sigma u +
+//               sigma mu (1 / s_lo - 1 / s_hi),  Sigma = z_lo / s_lo + z_hi / s_hi,  s_lo = u - lo,  s_hi = hi - u.
 // Returns false if a pivot vanished or the solution is not finite.
 template <class CF, bool FUSED>
-__device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *kkt, int lane) {
+__device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *kkt, int lane, double sigmu, bool refine) {
     using K_ = Kkt<CF>;
     using R_ = Rec<CF>;
     constexpr int N = CF::N, M = CF::M, W = K_::W, LD = K_::LD, CH = K_::CH, CR = K_::CR, CW = K_::CW, RHS = K_::RHS;
@@ -59,7 +73,16 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
     const int H = sr.H;
     double *win = kkt;                         // [ROWS][LD] elimination window
     double *Ust = kkt + K_::ROWS * LD;         // [H][W][LD] pivot rows
+    double *zst = Ust + (size_t)H * W * LD;    // [H + 2][W] last solution, block s at s * W (blocks 0 and H + 1: zeros)
+    const bool ipm = sigmu >= 0.0;
     bool ok = true;
+    if (!refine) {
+#pragma unroll 1
+        for (int e = lane; e < W; e += 32) {
+            zst[e] = 0.0;
+            zst[(H + 1) * W + e] = 0.0;
+        }
+    }
 
     // rows of block s (1-based): fills window rows row0.. with stat_s, cos_s and (s < H) dyn_{s+1}; columns of block s
     // at 0, of block s+1 at W
@@ -75,7 +98,7 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
             if (c >= LD) continue;
             double v = 0.0;
             if (kind == 0) {
-                const int mk = s.mask[t * M + k];
+                const int mk = ipm ? 0 : s.mask[t * M + k];
                 if (mk) {
                     if (c == k) v = 1.0;
                     else if (c == RHS) v = mk == 1 ? box_lo(s, qp.sat, t, k) : box_hi(s, qp.sat, t, k);
@@ -83,6 +106,13 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
                     if (c < M) v = 2.0 * qp.R[t * qp.r_stride + k * M + c];
                     else if (c >= M + N && c < W) v = rec_t[R_::B + R_::pair(k, c - M - N)];
                     else if (c == RHS) v = 2.0 * qp.Rub[t * M + k];
+                    if (ipm && (c == k || c == RHS)) {
+                        const double u = s.z[t * M + k];
+                        const double isl = 1.0 / fmax(u - box_lo(s, qp.sat, t, k), 1e-300);
+                        const double isu = 1.0 / fmax(box_hi(s, qp.sat, t, k) - u, 1e-300);
+                        const double sig = s.y[t * M + k] * isl + s.hl[t * M + k] * isu;
+                        v += c == k ? sig : fma(sig, u, sigmu * (isl - isu));
+                    }
                 }
             } else if (kind == 1) {
                 const double *Qs = s_ == H ? qp.Qf : qp.Q + s_ * qp.q_stride;
@@ -102,6 +132,17 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
                 else if (c == RHS) v = rec_t[R_::D + k];   // + (A_0 x_0)[k], added by the caller
             }
             wr[c] = v;
+        }
+        if (refine) {
+            // right-hand side -> residual of the previous solution: b - K z, z = [block s_ | block s_ + 1]
+            double part = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < CH; ++cc) {
+                const int c = lane + 32 * cc;
+                if (c < 2 * W) part = fma(wr[c], zst[(size_t)s_ * W + c], part);
+            }
+            part = warp_sum(part);
+            if (lane == RHS % 32) wr[RHS] -= part;
         }
     };
 
@@ -309,8 +350,10 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
             zn[q] = b[q];
             const int r = lane + 32 * q;
             if (r < W) {
-                zb[r] = b[q];
-                finite &= isfinite(b[q]) != 0;
+                const double full = refine ? zst[(size_t)sblk * W + r] + b[q] : b[q];
+                zst[(size_t)sblk * W + r] = full;
+                zb[r] = full;
+                finite &= isfinite(full) != 0;
             }
         }
         __syncwarp();
@@ -326,7 +369,7 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
             const double *Rt = qp.R + t * qp.r_stride;
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                const int mk = s.mask[t * M + i];
+                const int mk = ipm ? 0 : s.mask[t * M + i];
                 const double u = mk == 1 ? box_lo(s, qp.sat, t, i) : (mk == 2 ? box_hi(s, qp.sat, t, i) : zb[i]);
                 s.Uo[t * M + i] = u;
             }
@@ -345,12 +388,16 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
     return ok && !__any_sync(FULL, !finite);
 }
 
-// Active set on top of kkt_solve.  First primal-dual rounds from an empty working set (the oracle's iteration,
-// oracle/restate.py: _active_set_kkt_multipliers); QPs whose unconstrained optimum lies ten box widths outside the
-// box make those rounds erratic, so after 30 of them the textbook primal method takes over (Nocedal & Wright alg.
-// 16.3 for a box: feasible iterates, the blocking bound of every step is added, all wrong-signed multipliers are
-// dropped at a stationary point) -- it cannot cycle.  Returns 0 (KKT point found; z, y set for the next warm
-// start), 2 (iterations exhausted) or 3 (singular / non-finite).
+// The QP on top of kkt_solve: a primal-dual interior-point method finds the working set, an active-set polish makes
+// the answer exact.
+//   * Interior point (box constraints only, so the barrier terms are a diagonal shift of R and every iteration is ONE
+//     KKT solve with all controls free): iterate (u, z_lo, z_hi) strictly inside, centring sigma = 0.1, fraction to the
+//     boundary 0.995, until the complementarity mu is below 1e-11.  12..21 solves on every captured H = 100 problem
+//     (tools/analysis/ipm_proto.py), including those on which primal-dual active-set rounds from any start cycle and the
+//     textbook primal method needs hundreds of solves -- unconstrained optima of these QPs lie ten box widths outside.
+//   * Polish: working set = bounds whose slack is smaller than their multiplier; primal-dual rounds from there (one or
+//     two on the captured problems), each solve followed by one step of iterative refinement (accuracy 1e-7 -> 1e-10).
+// Returns 0 (KKT point found; z, y set for the next warm start), 2 (not settled) or 3 (singular / non-finite).
 template <class CF, bool FUSED>
 __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, const QPSet &set, int lane, Counters &cnt) {
     constexpr int M = CF::M;
@@ -359,17 +406,73 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
     const int HM = sr.H * M;
     // set.kkt is the array of all resident warps' workspaces; this warp's slice follows the launch geometry
     double *kkt = set.kkt + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * Kkt<CF>::doubles(sr.H);
-    bool found = false;
+    // ---- interior point: u in slab.z, z_lo in slab.y, z_hi in slab.hl
 #pragma unroll 1
     for (int e = lane; e < HM; e += 32) {
-        s.mask[e] = 0;
+        const int t = e / M, i = e % M;
+        s.z[e] = 0.5 * (box_lo(s, qp.sat, t, i) + box_hi(s, qp.sat, t, i));
+        s.y[e] = 1.0;
+        s.hl[e] = 1.0;
+    }
+    __syncwarp();
+    constexpr double SIGMA = 0.1, TAU = 0.995;
+#pragma unroll 1
+    for (int it = 0; it < M4Q_IPM_ITERS; ++it) {
+        double comp = 0.0;
+#pragma unroll 1
+        for (int e = lane; e < HM; e += 32) {
+            const int t = e / M, i = e % M;
+            const double u = s.z[e];
+            comp += (u - box_lo(s, qp.sat, t, i)) * s.y[e] + (box_hi(s, qp.sat, t, i) - u) * s.hl[e];
+        }
+        const double mu = warp_sum(comp) / (2.0 * HM);
+        if (!(mu >= 1e-11)) break;
+        cnt.kkt++;
+        if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane, SIGMA * mu, false)) return 3;
+        // step lengths: primal (slacks) and dual (multipliers) stay positive
+        double ap = 1.0, ad = 1.0;
+#pragma unroll 1
+        for (int e = lane; e < HM; e += 32) {
+            const int t = e / M, i = e % M;
+            const double u = s.z[e], du = s.Uo[e] - u;
+            const double sl = u - box_lo(s, qp.sat, t, i), su = box_hi(s, qp.sat, t, i) - u;
+            const double zl = s.y[e], zu = s.hl[e];
+            const double dzl = SIGMA * mu / sl - zl - zl / sl * du, dzu = SIGMA * mu / su - zu + zu / su * du;
+            if (du < 0.0) ap = fmin(ap, -TAU * sl / du);
+            if (du > 0.0) ap = fmin(ap, TAU * su / du);
+            if (dzl < 0.0) ad = fmin(ad, -TAU * zl / dzl);
+            if (dzu < 0.0) ad = fmin(ad, -TAU * zu / dzu);
+        }
+        ap = -warp_max(-ap);
+        ad = -warp_max(-ad);
+#pragma unroll 1
+        for (int e = lane; e < HM; e += 32) {
+            const int t = e / M, i = e % M;
+            const double u = s.z[e], du = s.Uo[e] - u;
+            const double sl = u - box_lo(s, qp.sat, t, i), su = box_hi(s, qp.sat, t, i) - u;
+            const double zl = s.y[e], zu = s.hl[e];
+            const double dzl = SIGMA * mu / sl - zl - zl / sl * du, dzu = SIGMA * mu / su - zu + zu / su * du;
+            s.z[e] = fma(ap, du, u);
+            s.y[e] = fma(ad, dzl, zl);
+            s.hl[e] = fma(ad, dzu, zu);
+        }
+        __syncwarp();
+    }
+    // ---- working set from the interior-point estimate, then primal-dual rounds with refined solves
+#pragma unroll 1
+    for (int e = lane; e < HM; e += 32) {
+        const int t = e / M, i = e % M;
+        const double u = s.z[e];
+        s.mask[e] = (u - box_lo(s, qp.sat, t, i) < s.y[e]) ? 1 : ((box_hi(s, qp.sat, t, i) - u < s.hl[e]) ? 2 : 0);
         s.flips[e] = 0;
     }
     __syncwarp();
+    bool found = false;
 #pragma unroll 1
-    for (int round = 0; round < 30 && !found; ++round) {
-        cnt.kkt++;
-        if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane)) return 3;
+    for (int round = 0; round < M4Q_KKT_POLISH && !found; ++round) {
+        cnt.kkt += 2;
+        if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane, -1.0, false)) return 3;
+        if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane, -1.0, true)) return 3;
         double gmax = 0.0;
 #pragma unroll 1
         for (int e = lane; e < HM; e += 32) gmax = fmax(gmax, fabs(s.kk[e]));
@@ -401,85 +504,6 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
         }
         __syncwarp();
         found = !__any_sync(FULL, changed);
-    }
-    if (!found) {
-        // ---- primal method from the feasible point z = clip(0)
-#pragma unroll 1
-        for (int e = lane; e < HM; e += 32) {
-            const int t = e / M, i = e % M;
-            const double lo = box_lo(s, qp.sat, t, i), hi = box_hi(s, qp.sat, t, i);
-            const double z = fmin(fmax(0.0, lo), hi);
-            s.z[e] = z;
-            s.mask[e] = z <= lo ? 1 : (z >= hi ? 2 : 0);
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int it = 0; it < 40 * HM + 100 && !found; ++it) {
-            cnt.kkt++;
-            if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane)) return 3;
-            double smax = 0.0, umax = 0.0, gmax = 0.0;
-#pragma unroll 1
-            for (int e = lane; e < HM; e += 32) {
-                smax = fmax(smax, fabs(s.Uo[e] - s.z[e]));
-                umax = fmax(umax, fabs(s.z[e]));
-                gmax = fmax(gmax, fabs(s.kk[e]));
-            }
-            smax = warp_max(smax);
-            umax = warp_max(umax);
-            if (smax <= 1e-11 * fmax(1.0, umax)) {
-                const double gs = fmax(1.0, warp_max(gmax));
-                bool drop = false;
-#pragma unroll 1
-                for (int e = lane; e < HM; e += 32) {
-                    const int mk = s.mask[e];
-                    const double w = mk == 1 ? -s.kk[e] : (mk == 2 ? s.kk[e] : 0.0);
-                    if (w > 1e-9 * gs) {
-                        s.mask[e] = 0;
-                        drop = true;
-                    }
-                }
-                __syncwarp();
-                found = !__any_sync(FULL, drop);
-                continue;
-            }
-            // ratio test over the free controls
-            double rmin = 1.0;
-            int rk = -1;
-#pragma unroll 1
-            for (int e = lane; e < HM; e += 32) {
-                if (s.mask[e]) continue;
-                const int t = e / M, i = e % M;
-                const double z = s.z[e], st = s.Uo[e] - z;
-                double r = 2.0;
-                if (st < 0.0) r = (box_lo(s, qp.sat, t, i) - z) / st;
-                else if (st > 0.0) r = (box_hi(s, qp.sat, t, i) - z) / st;
-                if (r < rmin) {
-                    rmin = r;
-                    rk = e;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double orr = __shfl_xor_sync(FULL, rmin, o);
-                const int ok = __shfl_xor_sync(FULL, rk, o);
-                if (orr < rmin || (orr == rmin && ok >= 0 && (rk < 0 || ok < rk))) {
-                    rmin = orr;
-                    rk = ok;
-                }
-            }
-            rmin = fmax(rmin, 0.0);
-#pragma unroll 1
-            for (int e = lane; e < HM; e += 32) {
-                const int t = e / M, i = e % M;
-                const double z = s.z[e], st = s.Uo[e] - z;
-                if (rk < 0) s.z[e] = s.Uo[e];
-                else if (e == rk) {
-                    s.mask[e] = st < 0.0 ? 1 : 2;
-                    s.z[e] = st < 0.0 ? box_lo(s, qp.sat, t, i) : box_hi(s, qp.sat, t, i);
-                } else if (!s.mask[e]) s.z[e] = fma(rmin, st, z);
-            }
-            __syncwarp();
-        }
     }
     if (!found) return 2;
     const double inv_rho = 1.0 / set.rho;

@@ -257,18 +257,25 @@ def test_order1_h100_matches_reference():
                            fidelity_restatement=float(g['fidelity_restatement'])), fh, indent=1)
 
 
-def test_order1_h100_ensemble_all_exit_zero():
-    """256 perturbed transmons at H = 100, order 1: every member completes (exit code 0) and a member run alone
-    reproduces its ensemble result bit for bit (the KKT workspaces are per resident warp)."""
-    cfg = systems.config_transmon(1, horizon=100, n_steps=8)
+def test_order1_h100_ensemble_exit_codes():
+    """512 perturbed transmons at H = 100, order 1, 12 steps (round 1: every member exit code 2 from the fourth step on).
+    Now at least 98 % complete with exit code 0; the rest end with the reference's solver-warning code 2, never with
+    garbage: on those members the guess trajectory itself has left the model's range (|x| ~ 4e4 for a density matrix)
+    and the QP linearised around it defeats the CPU solvers as well (profiles/r2_h100_order1_analysis.md: interior
+    point and active set disagree by 3e-2 on the QP member 96 fails on; measured 18 of 2,368 members over 20 steps).
+    A member run alone reproduces its ensemble result bit for bit (the KKT workspaces are per resident warp)."""
+    cfg = systems.config_transmon(1, horizon=100, n_steps=12)
     ens, _ = systems.ensemble_transmon(65536)
     args, kw = systems.mpc_args(cfg)
     kw.pop('progress_bar')
-    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 256), *args[7:], fid_target=cfg['target'], **kw)
-    assert (res.exit_code == 0).all(), np.bincount(res.exit_code)
-    assert (res.steps_done == 8).all()
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(0, 512), *args[7:], fid_target=cfg['target'], **kw)
+    assert np.isin(res.exit_code, (0, 2)).all(), np.bincount(res.exit_code)
+    done = res.exit_code == 0
+    assert done.mean() >= 0.98, np.bincount(res.exit_code)
+    assert (res.steps_done[done] == 12).all()
+    assert np.abs(res.us).max() <= cfg['sat'] + 1e-12 and np.isfinite(res.xs).all()
     one = m4q.mpc_ensemble(args[0], *args[1:6], ens.slice(37, 38), *args[7:], fid_target=cfg['target'], **kw)
-    assert np.array_equal(one.us[0], res.us[37])
+    assert res.exit_code[37] == 0 and np.array_equal(one.us[0], res.us[37])
 
 
 # ----------------------------------------------------------------------------------------------------------
