@@ -1796,8 +1796,8 @@ static int check_problem(const m4q_mpc_problem *p) {
     if (p->d < 0 || p->d * p->d > 32) return fail("plant dimension out of range (d*d <= 32)");
     if (p->d == 0 && p->lift_mode != M4Q_LIFT_IDENTITY) return fail("d = 0 (external plant) goes with the identity lift");
     if (p->d > 0 && p->lift_mode == M4Q_LIFT_IDENTITY && p->d * p->d != p->c) return fail("identity lift needs d*d == c");
-    if (p->lift_mode == M4Q_LIFT_COUPLED && !((p->d == 4 && p->c == 8) || (p->d == 9 && p->c == 18)))
-        return fail("coupled lift needs d = dA^2 and c = 2 dA^2");
+    if (p->lift_mode == M4Q_LIFT_COUPLED && !(p->d == 4 && p->c == 8))
+        return fail("coupled lift: two qubits (d = 4, c = 8) is the compiled case");
     if (p->lift_mode == M4Q_LIFT_TRUNC32 && !(p->d == 3 && p->c == 4)) return fail("trunc32 lift needs d = 3, c = 4");
     if (p->model_mode != M4Q_MODEL_TAYLOR && p->model_mode != M4Q_MODEL_EXACT) return fail("unknown model_mode");
     if (p->model_mode == M4Q_MODEL_EXACT && p->p != p->m)

@@ -192,3 +192,33 @@ def test_exact_model_oracle_against_finite_differences(unit_golden):
         u = 0.3 * U[:, 0]
         err = np.abs(bm.step(X[:, 0], u) - model.step(X[:, 0], u)).max() / np.abs(X[:, 0]).max()
         assert err < tol, (order, err)
+
+
+def test_h100_order1_oracle_and_its_costate_multipliers():
+    """BASELINE config 3 at H = 100, order 1 (tests/golden/qp_h100.npz, from the reference loop): the oracle re-solves
+    the captured QPs to the recorded answer, and the last-resort active set -- multipliers taken from the costates of
+    the sparse KKT solve instead of an adjoint sweep through prod A_t (noise floor eps ||prod A_t||^2) -- lands on the
+    same optimum.  The costate gradient agrees with the adjoint gradient where the latter still has digits."""
+    g = load_golden('qp_h100')
+    H = g['h100_U'].shape[2]
+    Q_ls, R_ls = [g['h100_Q']] * H + [g['h100_Qf']], [g['h100_R']] * H
+    sat, du = float(g['h100_sat']), float(g['h100_du'])
+    i = int(np.argmax(g['h100_step']))          # the mildest of them (step 9): seconds on one core
+    args = (g['h100_x_init'][i], g['h100_X_bm'][i], g['h100_U_bm'][i], Q_ls, R_ls, list(g['h100_A'][i]),
+            list(g['h100_B'][i]), list(g['h100_D'][i]), g['h100_u_prev'][i], sat, du)
+    X, U, obj, info = rs.qp_exact(*args)
+    assert np.abs(U - g['h100_U'][i]).max() < 1e-9
+    prob, lo, hi = info['prob'], info['lo'], info['hi']
+    X2, U2, g2 = rs._active_set_kkt_multipliers(prob, lo, hi)
+    assert np.abs(U2.T - U).max() < 1e-7
+    fixed = (U.T <= lo + 1e-13) | (U.T >= hi - 1e-13)
+    vals = np.where(U.T <= lo + 1e-13, lo, hi)
+    Xs, Us, gk = prob.solve_fixed(fixed, vals, want_grad=True)
+    ga = prob.gradient(Xs, Us)
+    assert np.abs(gk[~fixed]).max() < 1e-9                     # stationary on the free controls
+    assert np.abs(gk - ga).max() < 1e-4 * max(1.0, np.abs(ga).max())
+    # the loop fixture records how far two CPU evaluations of the same algorithm part, and the measured amplification
+    loop = load_golden('loop_transmon_o1_h100')
+    assert int(loop['exit_code']) == 0 and loop['us'].shape == (2, 20)
+    assert loop['restatement_gap_us'][:12].max() < 1e-8 < loop['restatement_gap_us'][-1]
+    assert loop['perturbation_gap_us'].shape == (3, 20)
