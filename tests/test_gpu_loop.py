@@ -281,6 +281,25 @@ def test_order1_h100_ensemble_exit_codes():
 # ----------------------------------------------------------------------------------------------------------
 # The rest of the reference's state-preparation matrix: other kernel instantiations
 # ----------------------------------------------------------------------------------------------------------
+def test_cnot_state_40_steps_match_reference():
+    """The first 40 steps of the 200-step CNOT ramp (tests/test_mpc4quantum.py:399-466; c = 16, m = 3, H = 50) against the
+    reference's own mpc() (oracle/make_golden_cnot.py; the reference run and its restatement agree to 7e-7 there):
+    controls within 1e-5, states within 1e-4, SQP counts per step equal."""
+    g = load_golden('loop_cnot')
+    n_steps = int(g['n_steps'])
+    cfg = systems.config_cnot(n_steps=n_steps, horizon=50, ramp_steps=200)
+    args, kw = systems.mpc_args(cfg)
+    (xs, us), _, ec = m4q.mpc(*args, **kw)
+    assert ec == 0 == int(g['exit_code'])
+    assert us.shape == g['us'].shape
+    assert np.abs(us - g['us']).max() < U_TOL, np.abs(us - g['us']).max(axis=0)
+    assert np.abs(xs - g['xs']).max() < 10 * U_TOL
+    plan_counts = m4q.mpc_ensemble(args[0], *args[1:6], m4q.EnsembleQExperiment(
+        cfg['experiment'].H0[None], np.array(cfg['experiment'].H1_list)[None], 'identity'), *args[7:],
+        **{k: v for k, v in kw.items() if k != 'progress_bar'}).qp_count[0]
+    assert np.array_equal(plan_counts, g['qp_per_step'])
+
+
 def test_cnot_state_16dim_three_controls():
     """tests/test_mpc4quantum.py:399-466: c = 16, m = 3 (n = 32: every lane a state row), H = 50, ramped target."""
     cfg = systems.config_cnot(n_steps=5, horizon=50, ramp_steps=200)
