@@ -349,6 +349,7 @@ struct QPSet {
 struct Counters {
     int admm, factor, polish, solves;
     int kkt;        // pivoted KKT solves (reported with the polish rounds)
+    int sticky;     // kkt_mode 2: a QP of this member broke down numerically in the Riccati path; later QPs skip it
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1513,7 +1514,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     bool run_admm = !set.polish || set.admm_first;
     const bool kkt_ok = set.kkt != nullptr && set.kkt_mode > 0 && set.polish;
     for (;;) {
-        if (kkt_ok && set.kkt_mode >= 2 && cnt.kkt > 0) {
+        if (kkt_ok && set.kkt_mode >= 2 && cnt.sticky) {
             // an earlier QP of this member needed the pivoted KKT solve (cost-to-go beyond fp64: order-1 model at long
             // horizons): go straight to it.  One factor call forms the stage operators A_t in the records.
             factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, 0.0, false, lane);
@@ -1561,6 +1562,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         }
         __syncwarp();
         bool certified = false;
+        bool numeric = false;   // the rounds ended on a settled working set whose solve is not stationary, or not finite
         for (int round = 0; round < set.max_polish; ++round) {
             factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, 0.0, true, lane);
             cnt.factor++;
@@ -1647,7 +1649,10 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
                 gmax = qp.q_diag ? riccati_solve<CF, FUSED>(sr, qp_in, 0.0, SWEEP_ADJOINT, false, lane)
                                  : adjoint_gradient<CF, FUSED>(sr, qp_in, lane);
             }
-            if (stable) break;
+            if (stable) {
+                numeric = !certified;
+                break;
+            }
         }
         if (certified) {
             // warm start of the next solve: z = u*, y = the (scaled) multipliers of the pinned controls
@@ -1665,7 +1670,30 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
         // not certified: (re)seed with an ADMM block at a tighter tolerance
         if (run_admm) eps *= 0.1;
         run_admm = true;
-        if (kkt_ok && (set.kkt_mode >= 2 || eps < 1e-10)) {
+        // The pivoted KKT solve takes over before the certificate would be relaxed, and (kkt_mode 2) as soon as the Riccati path
+        // breaks down NUMERICALLY -- a settled working set whose solve is not stationary or not finite: the cost-to-go
+        // has left the fp64 range (order-1 model at H = 100).  A working set that merely keeps moving is the ADMM
+        // re-seeding's business.
+        bool unstable = false;
+        if (kkt_ok && set.kkt_mode >= 2 && !numeric) {
+            // ... or the rollout shows that the linearised dynamics are unstable over the horizon (|x_t| grows by more
+            // than 1e3: a cost-to-go 1e6 times its O(1) part); the order-2 model at the same horizon stays O(1) and
+            // keeps the (much cheaper) ADMM re-seeding
+            const double *Xr = ws_Xo<CF>(sr);
+            double x0m = 0.0, xm = 0.0;
+            bool nf = false;
+#pragma unroll 1
+            for (int e = lane; e < (H + 1) * N; e += 32) {
+                const double v = fabs(Xr[e]);
+                nf |= !isfinite(v);
+                xm = fmax(xm, v);
+                if (e < N) x0m = fmax(x0m, v);
+            }
+            unstable = __any_sync(FULL, nf) || warp_max(xm) > 1e3 * fmax(warp_max(x0m), 1e-3);
+        }
+        // (with the KKT solve available the relaxed certificate below is never needed: four ADMM re-seedings, then KKT)
+        if (kkt_ok && ((set.kkt_mode >= 2 && (numeric || unstable)) || eps < 3e-6)) {
+            if (set.kkt_mode >= 2 && (numeric || unstable)) cnt.sticky = 1;
             status = kkt_active_set<CF, FUSED>(sr, qp_in, set, lane, cnt);
             x_nonfinite = false;
             break;
