@@ -417,12 +417,12 @@ def main():
     # DRAM traffic of the dominant kernel: from the committed ncu capture (profiles/), scaled to this launch's members
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')) as fh:
+        with open(os.path.join(ROOT, 'profiles', 'r2b_ncu_traffic.json')) as fh:
             tr = json.load(fh)
         if args.workload == 'transmon_h16':
             traffic = (tr['dram_bytes_read'] + tr['dram_bytes_write']) * n / tr['members']
             traffic_src = ('ncu dram__bytes_read.sum + dram__bytes_write.sum of one %d-member launch '
-                           '(profiles/r2_ncu_traffic.json), scaled by members' % tr['members'])
+                           '(profiles/r2b_ncu_traffic.json), scaled by members' % tr['members'])
     except (OSError, KeyError, ValueError):
         pass
     c_model = cfg['model'].dim_x if hasattr(cfg['model'], 'generators') else cfg['model'].A.shape[0]
@@ -483,6 +483,7 @@ def main():
                 todo.append(('transmon_h16', 1 << 20, 'BASELINE config 5: 1 M perturbed transmons on 8 GPUs, '
                                                      'fidelity histogram all-reduced over NCCL'))
             for name, nt, what in todo:
+                t_wl = time.time()
                 try:
                     rx_ = Runner(name, nt, rank, world)
                     key = name if nt != (1 << 20) else 'transmon_h16_1M'
@@ -492,6 +493,8 @@ def main():
                 except Exception as e:                      # a secondary workload never takes the headline down
                     wl[name] = {'error': repr(e)[:200], 'what': what}
                 torch.cuda.empty_cache()
+                if rank == 0:
+                    print('[bench] extra workload %s (%d members): %.1f s' % (name, nt, time.time() - t_wl), file=sys.stderr)
             extra['workloads'] = wl
     line['extra'] = extra
 
