@@ -54,8 +54,9 @@ typedef struct {
                             unknowns of one almost-block-diagonal system, row partial pivoting) with primal-dual active-set
                             rounds from an empty working set -- what the reference's sparse solver does, and the only thing
                             that works for the order-1 model at H = 100, where the cost-to-go leaves the fp64 range.
-                            2: the same as soon as the active-set rounds fail once, and from then on for every QP of that
-                            member.  Needs H (2n+m)(4n+2m+2) doubles per resident warp (n = 2c), which
+                            2: the same as soon as the Riccati path breaks down numerically (a settled working set whose
+                            solve is not stationary or not finite, or a rollout that grows by more than 1e3 over the
+                            horizon), and from then on for every QP of that member.  Needs H (2n+m)(4n+2m+2) doubles per resident warp (n = 2c), which
                             m4q_mpc_table_bytes / m4q_qp_workspace_bytes_kkt include when this is set. */
 } m4q_qp_settings;
 
