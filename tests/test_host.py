@@ -280,3 +280,28 @@ def test_shard_draws_equal_slices_of_the_full_draw():
     rng = np.random.default_rng(systems.ENSEMBLE_SEED)
     k = rng.uniform(0.9, 1.1, 64)
     assert np.array_equal(systems.ensemble_transmon(64)[1]['anharm_scale'], k)
+
+
+def test_kkt_workspaces_are_part_of_the_table_size_only_when_asked_for():
+    """m4q_qp_settings.kkt_fallback (include/m4q.h): the pivoted-KKT workspaces, H W (2W + 2) doubles per resident warp
+    plus the elimination window and the stored solution (W = 2n + m unknowns per stage), enter m4q_mpc_table_bytes /
+    m4q_qp_workspace_bytes_kkt only when the setting is on.  No device needed: the geometry falls back to 148 SMs."""
+    lib = _lib.lib()
+    c, m, H = 9, 2, 100
+    sizes = {}
+    for kkt in (0, 2):
+        pr = _lib.MpcProblem()
+        pr.c, pr.m, pr.p, pr.d, pr.horizon, pr.n_steps, pr.measure_freq = c, m, 2, 3, H, 20, 1
+        pr.n_targ, pr.sat = H + 21, 1.0
+        pr.qp = _lib.qp_settings(kkt_fallback=kkt)
+        sizes[kkt] = int(lib.m4q_mpc_table_bytes(ctypes.byref(pr)))
+        w, ctas, smem = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
+        assert lib.m4q_mpc_launch_info(ctypes.byref(pr), 0, ctypes.byref(w), ctypes.byref(ctas), ctypes.byref(smem)) == 0
+    assert sizes[0] > 0
+    n, W = 2 * c, 4 * c + m
+    per_warp = ((W + n) + H * W) * (2 * W + 2) + (H + 2) * W          # Kkt<CF>::doubles(H)
+    assert sizes[2] - sizes[0] == 8 * per_warp * w.value * ctas.value
+    base = int(lib.m4q_qp_workspace_bytes(4, c, m, H))
+    with_kkt = int(lib.m4q_qp_workspace_bytes_kkt(4, c, m, H))
+    assert base > 0 and (with_kkt - base) % (8 * per_warp) == 0 and with_kkt > base
+    assert _lib.qp_settings().kkt_fallback == 0
