@@ -511,7 +511,27 @@ def main():
                 qps += sum(x[1] for x in r)
                 k_done += cores
             cpu_t = time.perf_counter() - t0
+        # one process, one thread, a few members -> the per-core figure measured directly
+        single = None
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                t1 = time.perf_counter()
+                rs_ = [_cpu_member((args.workload, k, n_total)) for k in range(3)]
+                t_single = time.perf_counter() - t1
+            single = {'members': 3, 'threads': 1, 'trajectories_per_s': 3 / t_single,
+                      'qp_solves_per_s': sum(x[1] for x in rs_) / t_single}
+        except Exception as e:                                  # the multi-process figure above does not depend on this
+            single = {'error': repr(e)[:120]}
+        cpu_model = ''
+        try:
+            with open('/proc/cpuinfo') as fh:
+                cpu_model = next((ln.split(':', 1)[1].strip() for ln in fh if ln.startswith('model name')), '')
+        except OSError:
+            pass
         line['cpu_baseline'] = {
+            'host': {'cpu_count': os.cpu_count(), 'affinity': cores, 'model': cpu_model},
+            'single_process_single_thread': single,
             'value': k_done / cpu_t, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': 'first %d members of the same ensemble, %.1f s' % (k_done, cpu_t),
             'qp_solves_per_s': qps / cpu_t,
