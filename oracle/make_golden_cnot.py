@@ -1,7 +1,8 @@
 """CNOT state preparation (tests/test_mpc4quantum.py:399-466; c = 16, m = 3, H = 50, ramped target) through the
 reference's own mpc() -- TEST INFRASTRUCTURE ONLY; runs in the build container (needs /root/reference).
 
-    python -m oracle.make_golden_cnot [n_steps]
+    python -m oracle.make_golden_cnot [n_steps]        # closed loop through the reference's mpc()
+    python -m oracle.make_golden_cnot 40 tf            # teacher-forcing data of the same run (restated loop)
 
 Writes tests/golden/loop_cnot.npz: xs, us, SQP counts per step of the first n_steps (default 40) of the 200-step ramp,
 checked against the restated loop before it is written.
@@ -33,5 +34,29 @@ def main():
                         A_full=cfg['model'].A, x0=cfg['x0'], restatement_gap=gap, n_steps=n_steps)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and not (len(sys.argv) > 2 and sys.argv[2] == 'tf'):
     main()
+
+
+def teacher_forcing(n_steps=40):
+    """tests/golden/ens64_cnot.npz: what the controller knew at the start of every step of the run above and what it
+    answered (the format of oracle/make_golden_ens64.py, one member: the nominal plant), for the per-step parity test."""
+    cfg = systems.config_cnot(n_steps=n_steps, horizon=50, ramp_steps=200, discretize=rs.taylor_discretize)
+    stats = {'want_trace': True}
+    plant = rs.ExpmPlant(cfg['experiment'].H0, cfg['experiment'].H1_list)
+    xs, us, ec = rs.mpc_loop(cfg['x0'], cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'].dt,
+                             cfg['clock'].horizon, cfg['clock'].n_steps, plant, cfg['model'].A, cfg['Q'], cfg['R'],
+                             cfg['Qf'], cfg['sat'], cfg['du'], warm_start=cfg['warm_start'],
+                             measure_freq=cfg['clock'].measure_freq, stats=stats)
+    assert ec == 0
+    tr = stats['trace']
+    np.savez_compressed(os.path.join(OUT, 'ens64_cnot.npz'), us=us[None], xs=xs[None],
+                        qp_per_step=np.array(stats['qp_per_step'])[None],
+                        tf_x=np.array([t['x'] for t in tr])[None], tf_Xg=np.array([t['Xg'] for t in tr])[None],
+                        tf_Ug=np.array([t['Ug'] for t in tr])[None], tf_us=us[None],
+                        tf_qp_per_step=np.array(stats['qp_per_step'])[None])
+    print('== ens64_cnot: teacher-forcing data of %d steps' % n_steps)
+
+
+if __name__ == '__main__' and len(sys.argv) > 2 and sys.argv[2] == 'tf':
+    teacher_forcing(int(sys.argv[1]))

@@ -284,9 +284,10 @@ def test_order1_h100_ensemble_exit_codes():
 def test_cnot_state_40_steps_match_reference():
     """The first 40 steps of the 200-step CNOT ramp (tests/test_mpc4quantum.py:399-466; c = 16, m = 3, H = 50, order-1
     model) against the reference's own mpc() (oracle/make_golden_cnot.py).  SQP counts per step equal; controls within
-    1e-5 over the first 21 steps (achieved 2.8e-6; 7e-9 over the first 14).  From step 22 on single QPs are certified
-    against an adjoint gradient whose noise floor (eps ||prod A_t||^2, order-1 model at H = 50) sits above 1e-8 and come
-    out up to 3.2e-5 from the oracle (two CPU runs of the reference algorithm: 7e-7): held to 1e-4 there and recorded."""
+    1e-5 over the first 21 steps (achieved 2.8e-6; 7e-9 over the first 14) and within 1e-4 over all 40 (achieved 3.2e-5
+    at step 22).  The later gap is the loop, not the solver: replayed step by step from the reference run's own states
+    (tests/test_gpu_parity64.py::test_teacher_forced_steps_match_reference[cnot]) every one of the 40 steps agrees to
+    2e-12, and two CPU runs of the reference algorithm part by 7e-7 over the same 40 steps."""
     g = load_golden('loop_cnot')
     n_steps = int(g['n_steps'])
     cfg = systems.config_cnot(n_steps=n_steps, horizon=50, ramp_steps=200)
