@@ -392,7 +392,7 @@ __device__ __noinline__ bool kkt_solve(SlabRef sr, const QPData &qp_in, double *
 // the answer exact.
 //   * Interior point (box constraints only, so the barrier terms are a diagonal shift of R and every iteration is ONE
 //     KKT solve with all controls free): iterate (u, z_lo, z_hi) strictly inside, centring sigma = 0.1, fraction to the
-//     boundary 0.995, until the complementarity mu is below 1e-11.  12..21 solves on every captured H = 100 problem
+//     boundary 0.995, until the complementarity mu is below 1e-8 (1e-11 in a second pass if needed).  9..17 solves on every captured H = 100 problem
 //     (tools/analysis/ipm_proto.py), including those on which primal-dual active-set rounds from any start cycle and the
 //     textbook primal method needs hundreds of solves -- unconstrained optima of these QPs lie ten box widths outside.
 //   * Polish: working set = bounds whose slack is smaller than their multiplier; primal-dual rounds from there (one or
@@ -416,8 +416,15 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
     }
     __syncwarp();
     constexpr double SIGMA = 0.1, TAU = 0.995;
+    // two passes: the working set is read off at mu = 1e-8 (the same set as at 1e-11 on all but the odd problem, four
+    // solves earlier); if the polish does not settle from there the iteration carries on to 1e-11 and it is tried again
+    bool found = false;
+    int it = 0;
 #pragma unroll 1
-    for (int it = 0; it < M4Q_IPM_ITERS; ++it) {
+    for (int pass = 0; pass < 2 && !found; ++pass) {
+    const double mu_stop = pass == 0 ? 1e-8 : 1e-11;
+#pragma unroll 1
+    for (; it < M4Q_IPM_ITERS; ++it) {
         double comp = 0.0;
 #pragma unroll 1
         for (int e = lane; e < HM; e += 32) {
@@ -426,7 +433,7 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
             comp += (u - box_lo(s, qp.sat, t, i)) * s.y[e] + (box_hi(s, qp.sat, t, i) - u) * s.hl[e];
         }
         const double mu = warp_sum(comp) / (2.0 * HM);
-        if (!(mu >= 1e-11)) break;
+        if (!(mu >= mu_stop)) break;
         cnt.kkt++;
         if (!kkt_solve<CF, FUSED>(sr, qp_in, kkt, lane, SIGMA * mu, false)) return 3;
         // step lengths: primal (slacks) and dual (multipliers) stay positive
@@ -467,7 +474,6 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
         s.flips[e] = 0;
     }
     __syncwarp();
-    bool found = false;
 #pragma unroll 1
     for (int round = 0; round < M4Q_KKT_POLISH && !found; ++round) {
         cnt.kkt += 2;
@@ -505,6 +511,7 @@ __device__ __noinline__ int kkt_active_set(SlabRef sr, const QPData &qp_in, cons
         __syncwarp();
         found = !__any_sync(FULL, changed);
     }
+    }   // passes
     if (!found) return 2;
     const double inv_rho = 1.0 / set.rho;
 #pragma unroll 1
