@@ -56,7 +56,9 @@ typedef struct {
                             that works for the order-1 model at H = 100, where the cost-to-go leaves the fp64 range.
                             2: the same as soon as the Riccati path breaks down numerically (a settled working set whose
                             solve is not stationary or not finite, or a rollout that grows by more than 1e3 over the
-                            horizon), and from then on for every QP of that member.  Needs H (2n+m)(4n+2m+2) doubles per resident warp (n = 2c), which
+                            horizon), and from then on for every QP of that member.
+                            4: every QP goes to the KKT solve (no Riccati attempt): slow; for cross-checking the two
+                            solvers against each other on any problem.  Needs H (2n+m)(4n+2m+2) doubles per resident warp (n = 2c), which
                             m4q_mpc_table_bytes / m4q_qp_workspace_bytes_kkt include when this is set. */
 } m4q_qp_settings;
 

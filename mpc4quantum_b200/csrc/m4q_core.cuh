@@ -1514,7 +1514,7 @@ __device__ int qp_solve(SlabRef sr, const StageOps &ops_in, const QPData &qp_in,
     bool run_admm = !set.polish || set.admm_first;
     const bool kkt_ok = set.kkt != nullptr && set.kkt_mode > 0 && set.polish;
     for (;;) {
-        if (kkt_ok && set.kkt_mode >= 2 && cnt.sticky) {
+        if (kkt_ok && ((set.kkt_mode >= 2 && cnt.sticky) || set.kkt_mode >= 4)) {
             // an earlier QP of this member needed the pivoted KKT solve (cost-to-go beyond fp64: order-1 model at long
             // horizons): go straight to it.  One factor call forms the stage operators A_t in the records.
             factor_dispatch<CF, FUSED>(sr, ops_in, qp_in, 0.0, false, lane);

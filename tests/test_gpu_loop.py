@@ -257,6 +257,27 @@ def test_order1_h100_matches_reference():
                            fidelity_restatement=float(g['fidelity_restatement'])), fh, indent=1)
 
 
+def test_closed_loop_with_every_qp_through_the_kkt_solver():
+    """Cross-check of the two QP solvers inside the fused loop: the transmon loop of BASELINE config 3 (H = 16, 20 steps,
+    84 QPs) with every QP forced through the pivoted KKT solve + interior-point working set (kkt_fallback = 4, no
+    Riccati attempt) reproduces the reference fixture at the north_star tolerances, with the reference's SQP counts, and
+    agrees with the default (Riccati) path to 1e-7."""
+    g = load_golden('loop_transmon_o1')
+    cfg = systems.config_transmon(1)
+    args, kw = systems.mpc_args(cfg)
+    kw.pop('progress_bar')
+    ens = m4q.EnsembleQExperiment(np.asarray(cfg['experiment'].H0)[None], np.array(cfg['experiment'].H1_list)[None], 'identity')
+    res = m4q.mpc_ensemble(args[0], *args[1:6], ens, *args[7:], fid_target=cfg['target'],
+                           settings=m4q._lib.qp_settings(kkt_fallback=4), **kw)
+    ref = m4q.mpc_ensemble(args[0], *args[1:6], ens, *args[7:], fid_target=cfg['target'], **kw)
+    assert res.exit_code[0] == 0 and ref.exit_code[0] == 0
+    assert np.abs(res.us[0] - g['us']).max() < U_TOL
+    assert abs(res.fidelity[0] - float(g['fidelity'])) < F_TOL
+    assert np.array_equal(res.qp_count[0], g['qp_per_step'])
+    assert np.abs(res.us[0] - ref.us[0]).max() < 1e-7
+    assert res.counters[0, 1] < ref.counters[0, 1] or res.counters[0, 2] > ref.counters[0, 2]   # it did take the other path
+
+
 def test_order1_h100_ensemble_exit_codes():
     """512 perturbed transmons at H = 100, order 1, 12 steps (round 1: every member exit code 2 from the fourth step on).
     Now at least 98 % complete with exit code 0; the rest end with the reference's solver-warning code 2, never with

@@ -179,6 +179,29 @@ def test_quad_program_h100_order1_pivoted_kkt():
         assert np.abs(U - g['h100_U'][0]).max() < 1e-5
 
 
+@pytest.mark.parametrize('c,m', [(4, 1), (4, 2), (9, 2), (8, 2), (16, 3), (16, 1)])
+def test_pivoted_kkt_solver_all_instantiations(c, m):
+    """The pivoted stage-wise KKT solve + interior-point working set (csrc/m4q_kkt.cuh) forced on every QP
+    (kkt_fallback = 4: no Riccati attempt) for every compiled (dim_x, dim_u): random instances with diagonal and full
+    Hermitian costs, with and without the rate bound, against the exact oracle -- and against the default
+    (Riccati-based) path of the same library.  Block widths 2n + m = 9 .. 67: one to three unknowns per lane."""
+    from oracle import restate as rs
+    rng = np.random.default_rng(77 * c + m)
+    st = m4q._lib.qp_settings(kkt_fallback=4)
+    for H in (3, 12):
+        for hermitian_cost in (False, True):
+            for with_du in (True, False):
+                a = _random_qp(rng, c, m, H, hermitian_cost, with_du)
+                Xc, Uc, objc, info = rs.qp_exact(*a)
+                X, U, obj, qinfo = optimize.quad_program(*a, settings=st)
+                assert qinfo.status_code == 0, (c, m, H, hermitian_cost, with_du)
+                assert np.abs(U - Uc).max() < 1e-8, (c, m, H, hermitian_cost, with_du, np.abs(U - Uc).max())
+                assert np.abs(X - Xc).max() < 1e-7
+                assert abs(obj - objc) < 1e-8 * max(1.0, abs(objc))
+                X2, U2, obj2, _ = optimize.quad_program(*a)
+                assert np.abs(U - U2).max() < 1e-8
+
+
 def test_quad_program_batched_matches_single(qp_golden):
     g = qp_golden
     tag = 'transmon'
