@@ -23,6 +23,7 @@
 // array and is served by L1/L2.  This path is cold for every configuration that the Riccati path certifies.
 #pragma once
 
+// measurement aids (build variants): interior-point iteration cap, polish rounds per pass
 #ifndef M4Q_IPM_ITERS
 #define M4Q_IPM_ITERS 80
 #endif
