@@ -275,8 +275,9 @@ class ClosedLoopPlan:
             fidelity_sqrt=False):
         """Enqueue the closed loop for n members.  x0/H0/H1 are CUDA tensors (complex128).
 
-        A plan owns ONE set of tables (with the atomic work counter of the launch) and ONE set of output buffers: keep at
-        most one launch of a plan in flight; use one plan per stream for concurrent launches.
+        A plan owns ONE set of tables (with the atomic work counter of the launch) and ONE set of output buffers: launches
+        of one plan are serialised (a launch on another stream waits for the previous one); use one plan per stream for
+        concurrent launches, and read the results of a launch before the next one of the same plan overwrites them.
         Results of members that stop early (exit codes 1/2/3) are zero beyond ``steps_done``.
         streaming = (A [n, c, c (p+1)], P [n, dz, dz], discount): per-member OnlineDMDc state, updated in place."""
         n = self.capacity if n is None else int(n)
@@ -300,10 +301,18 @@ class ClosedLoopPlan:
             raise ValueError('%d members but %d initial states (pass x0_shared=True for one shared state)' % (n, x0.shape[0]))
         step_end = self.S if step_end is None else step_end
         partial = step_begin > 0 or step_end < self.S
+        # one launch of a plan in flight at a time: the tables (work counter), workspaces and output buffers belong to the
+        # plan, so a launch on another stream first waits for the previous one (same stream: ordered anyway)
+        t = _lib.torch()
+        st = stream if stream is not None else t.cuda.current_stream()
+        last = getattr(self, '_last_launch', None)
+        if last is not None:
+            st.wait_event(last)
         if step_begin == 0:
-            self.xs[:n].zero_()
-            self.us[:n].zero_()
-            self.qp_count[:n].zero_()
+            with t.cuda.stream(st):          # on the launch stream, not on whatever stream is current
+                self.xs[:n].zero_()
+                self.us[:n].zero_()
+                self.qp_count[:n].zero_()
         self.prob.noise_sigma, self.prob.noise_seed = float(noise_sigma), int(noise_seed) & (2 ** 64 - 1)
         self.prob.member_offset = int(member_offset)
         self.prob.fidelity_sqrt = int(bool(fidelity_sqrt))
@@ -319,6 +328,8 @@ class ClosedLoopPlan:
             _lib.ptr(self.exit_code), _lib.ptr(self.steps_done), _lib.ptr(self.qp_count), _lib.ptr(self.counters),
             _lib.ptr(self.fidelity), _lib.ptr(self.state) if (partial or self.external) else _lib.c_vp(None),
             _lib.ptr(self.tables), _lib.stream_ptr(stream)))
+        self._last_launch = t.cuda.Event()
+        self._last_launch.record(st)
         return EnsembleResult(xs=self.xs[:n], us=self.us[:n], exit_code=self.exit_code[:n],
                               steps_done=self.steps_done[:n], qp_count=self.qp_count[:n], counters=self.counters[:n],
                               fidelity=None if self.fidelity is None else self.fidelity[:n],

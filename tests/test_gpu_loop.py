@@ -278,6 +278,34 @@ def test_closed_loop_with_every_qp_through_the_kkt_solver():
     assert res.counters[0, 1] < ref.counters[0, 1] or res.counters[0, 2] > ref.counters[0, 2]   # it did take the other path
 
 
+def test_launches_of_one_plan_on_two_streams_are_serialised():
+    """A plan owns one set of tables (the atomic work counter), workspaces and outputs; a second launch on another stream
+    waits for the first instead of racing it (round-1 advisor finding).  Both launches give the single-stream answer."""
+    import torch
+    from mpc4quantum_b200 import _lib
+    from mpc4quantum_b200.mpc import ClosedLoopPlan
+    cfg = systems.config_transmon(1, horizon=8, n_steps=5)
+    ens, _ = systems.ensemble_transmon(65536)
+    n = 3000
+    sub = ens.slice(0, n)
+    plan = ClosedLoopPlan(cfg['dim_u'], cfg['order'], cfg['X_targ'], cfg['U_targ'], cfg['clock'], cfg['model'], cfg['Q'],
+                          cfg['R'], cfg['Qf'], cfg['sat'], cfg['du'], d=3, warm_start=cfg['warm_start'],
+                          fid_target=cfg['target'], capacity=n)
+    H0, H1 = _lib.dev(sub.H0, np.complex128), _lib.dev(sub.H1, np.complex128)
+    x0 = _lib.dev(np.asarray(cfg['x0']).reshape(1, -1), np.complex128)
+    ref = plan.run(x0, H0, H1, n=n, x0_shared=True)
+    torch.cuda.synchronize()
+    us_ref = ref.us.clone()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    s1.wait_stream(torch.cuda.current_stream())
+    s2.wait_stream(torch.cuda.current_stream())
+    plan.run(x0, H0, H1, n=n, x0_shared=True, stream=s1)
+    res = plan.run(x0, H0, H1, n=n, x0_shared=True, stream=s2)      # no host synchronisation in between
+    torch.cuda.synchronize()
+    assert (res.exit_code == 0).all() and (res.steps_done == 5).all()
+    assert torch.equal(res.us, us_ref)
+
+
 def test_order1_h100_ensemble_exit_codes():
     """512 perturbed transmons at H = 100, order 1, 12 steps (round 1: every member exit code 2 from the fourth step on).
     Now at least 98 % complete with exit code 0; the rest end with the reference's solver-warning code 2, never with
