@@ -222,3 +222,39 @@ def test_h100_order1_oracle_and_its_costate_multipliers():
     assert int(loop['exit_code']) == 0 and loop['us'].shape == (2, 20)
     assert loop['restatement_gap_us'][:12].max() < 1e-8 < loop['restatement_gap_us'][-1]
     assert loop['perturbation_gap_us'].shape == (3, 20)
+
+
+def test_kkt_interior_point_model_of_the_device_solver():
+    """oracle/kkt_model.py (the numpy statement of csrc/m4q_kkt.cuh: stage-ordered KKT system, pivoted LU, interior-point
+    working set, refined polish) against the exact oracle: a random short QP with a full Hermitian cost, and the QP of
+    step 9 of the reference loop at H = 100 with the order-1 model (||prod A_t|| = 5e7, 23 controls on a bound)."""
+    from oracle import kkt_model as km
+    rng = np.random.default_rng(5)
+    c, m, H = 4, 2, 12
+
+    def crandn(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    A_ls = [np.eye(c) + 0.2 * crandn(c, c) / np.sqrt(c) for _ in range(H)]
+    B_ls = [0.4 * crandn(c, m) for _ in range(H)]
+    D_ls = [0.05 * crandn(c, 1) for _ in range(H)]
+    L = crandn(c, c) / np.sqrt(c)
+    Q = L @ L.conj().T
+    R = 0.05 * np.eye(m)
+    args = (crandn(c), crandn(c, H + 1), 0.3 * rng.standard_normal((m, H)), [Q] * (H + 1), [R] * H, A_ls, B_ls, D_ls,
+            0.3 * rng.standard_normal(m), 0.6, 0.25)
+    X, U, obj, info = rs.qp_exact(*args)
+    Uk, stats = km.qp_kkt_ipm(info['prob'], info['lo'], info['hi'])
+    assert Uk is not None and stats['polish_rounds'] <= 3 and stats['ipm_solves'] <= 25
+    assert np.abs(Uk.T - U).max() < 1e-9
+    assert (np.abs(np.abs(U) - 0.6) < 1e-12).sum() >= 3          # the box is active in this instance
+    g = load_golden('qp_h100')
+    Hh = g['h100_U'].shape[2]
+    i = int(np.argmax(g['h100_step']))
+    args = (g['h100_x_init'][i], g['h100_X_bm'][i], g['h100_U_bm'][i], [g['h100_Q']] * Hh + [g['h100_Qf']],
+            [g['h100_R']] * Hh, list(g['h100_A'][i]), list(g['h100_B'][i]), list(g['h100_D'][i]), g['h100_u_prev'][i],
+            float(g['h100_sat']), float(g['h100_du']))
+    prob = rs._SparseQP(np.asarray(args[0]).reshape(-1), *args[1:8])
+    lo, hi = rs.qp_bounds(args[2], args[8], args[9], args[10])
+    Uk, stats = km.qp_kkt_ipm(prob, lo.T.copy(), hi.T.copy())
+    assert Uk is not None and stats['ipm_solves'] <= 25
+    assert np.abs(Uk.T - g['h100_U'][i]).max() < 1e-7
