@@ -23,7 +23,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 N_MEMBERS = 64
-MEMBERS = {'transmon_h50': 16, 'transmon_h100': 8}      # the long-horizon oracle QPs cost ~0.4 s each
+MEMBERS = {'transmon_h50': 16, 'transmon_h100': 16}      # the long-horizon oracle QPs cost ~0.4 s each
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
 

@@ -227,7 +227,7 @@ def test_order1_h100_matches_reference():
     closed-loop comparison is therefore held to the north_star tolerance on the steps before that amplification sets in
     (the 1e-10 perturbation still below 1e-9: steps 0..6); every step of 8 perturbed members is pinned on its own,
     without the loop in between, by tests/test_gpu_parity64.py::test_teacher_forced_steps_match_reference
-    [transmon_h100] (achieved 9e-8)."""
+    [transmon_h100] (16 members, achieved 1.8e-7)."""
     g = load_golden('loop_transmon_o1_h100')
     cfg = systems.config_transmon(1, horizon=100, n_steps=20)
     args, kw = systems.mpc_args(cfg)
