@@ -225,7 +225,7 @@ def test_order1_h100_matches_reference():
     QP solution (step 4) by 1e-12 / 1e-10 changes the applied controls by 2e-4 / 0.3 at step 19 and by 2e-11 / 2e-6
     already at step 8; the reference run and its numpy restatement, which share the QP code, part by 1e-3.  A
     closed-loop comparison is therefore held to the north_star tolerance on the steps before that amplification sets in
-    (the 1e-10 perturbation still below 1e-9: steps 0..6); every step of 8 perturbed members is pinned on its own,
+    (the 1e-10 perturbation still below 1e-9: steps 0..6); every step of 16 perturbed members is pinned on its own,
     without the loop in between, by tests/test_gpu_parity64.py::test_teacher_forced_steps_match_reference
     [transmon_h100] (16 members, achieved 1.8e-7)."""
     g = load_golden('loop_transmon_o1_h100')

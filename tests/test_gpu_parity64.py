@@ -49,7 +49,7 @@ CONFIGS = {
 TF_CONFIGS = dict(CONFIGS, transmon_h50=(lambda: systems.config_transmon(1, horizon=50, n_steps=20),
                                          systems.ensemble_transmon, 65536),
                   # H = 100: ||prod A_t|| ~ 4e13, every QP from the fourth step on goes through the pivoted KKT solve
-                  # (csrc/m4q_kkt.cuh); 8 members x 20 steps
+                  # (csrc/m4q_kkt.cuh); 16 members x 20 steps
                   transmon_h100=(lambda: systems.config_transmon(1, horizon=100, n_steps=20),
                                  systems.ensemble_transmon, 65536),
                   # CNOT state (c = 16, m = 3, H = 50, order-1 model): the 40 steps of tests/golden/loop_cnot.npz, nominal
