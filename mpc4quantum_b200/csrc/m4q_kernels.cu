@@ -1623,6 +1623,13 @@ static int plan(KernelT kernel, int max_warps, int slab_doubles, int shared_doub
         const int w = atoi(ov);
         if (w >= 1 && w < warps) warps = w;
     }
+    // Less than one round of resident warps: spread the members over all SMs (narrower CTAs) instead of filling some SMs
+    // and leaving the others empty -- a member's speed depends on how many warps share its SM's pipes and caches
+    // (592 order-1 H = 100 members: 148 CTAs x 4 warps instead of 60 x 10; 4,096 qubits: 148 x 28 instead of 128 x 32)
+    if (!getenv("M4Q_MAX_WARPS") && n_units > 0 && n_units < (long long)sms * warps) {
+        const int w = (int)((n_units + sms - 1) / sms);
+        warps = w < 1 ? 1 : w;
+    }
     g->slab_doubles = slab_doubles;
     g->shared_doubles = shared_doubles;
     int per_sm = 1;
