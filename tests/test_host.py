@@ -85,7 +85,11 @@ def test_launch_geometry_without_a_device():
     assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 8192, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
     assert w.value == 14        # 8192 = 3.95 rounds of 148 x 14 instead of 3.46 rounds of 148 x 16
     assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 100, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
-    assert w.value == 16 and c.value == 7
+    assert w.value == 1 and c.value == 100      # less than one round of resident warps: spread over the SMs
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 592, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert w.value == 4 and c.value == 148
+    assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 2000, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == 0
+    assert w.value == 14 and c.value == 143     # ceil(2000 / 148) warps per CTA, ceil(2000 / 14) CTAs
     prob.horizon = 400          # does not fit the shared-memory slab: refused, not truncated
     assert lib.m4q_mpc_launch_info(ctypes.byref(prob), 0, ctypes.byref(w), ctypes.byref(c), ctypes.byref(s)) == -1
 
