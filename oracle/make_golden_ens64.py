@@ -23,7 +23,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 N_MEMBERS = 64
-MEMBERS = {'transmon_h50': 16, 'transmon_h100': 16}      # the long-horizon oracle QPs cost ~0.4 s each
+MEMBERS = {'transmon_h50': 16, 'transmon_h100': 16, 'transmon_o2_h100': 8}      # the long-horizon oracle QPs cost ~0.4 s each
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
 
@@ -39,6 +39,8 @@ def make_cfg(name):
         return systems.config_transmon(1, horizon=50, n_steps=20, discretize=disc), systems.ensemble_transmon(65536)[0]
     if name == 'transmon_h100':  # order-1 model at H = 100: cost-to-go beyond fp64, the device solves a pivoted KKT system
         return systems.config_transmon(1, horizon=100, n_steps=20, discretize=disc), systems.ensemble_transmon(65536)[0]
+    if name == 'transmon_o2_h100':  # the same horizon with the order-2 model (||A_t|| ~ 1.02: the Riccati path certifies)
+        return systems.config_transmon(2, horizon=100, n_steps=20, discretize=disc), systems.ensemble_transmon(65536)[0]
     if name == 'crosstalk':     # the config's own S = 50 (round 1 pinned S = 12 only)
         return systems.config_crosstalk(0.0, discretize=disc), systems.ensemble_crosstalk(65536)[0]
     raise SystemExit('unknown config %s' % name)

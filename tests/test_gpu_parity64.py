@@ -34,7 +34,7 @@ pytestmark = pytest.mark.gpu
 
 U_TOL, F_TOL, TF_TOL = 1e-5, 1e-6, 1e-8
 REPRO_TOL = 1e-8          # reference mpc() vs its numpy restatement: below this the member's closed loop is reproducible
-MIN_REPRODUCIBLE = {'qubit': 30, 'transmon': 64, 'crosstalk': 50}
+MIN_REPRODUCIBLE = {'qubit': 30, 'transmon': 64, 'crosstalk': 50, 'transmon_o2_h100': 8}
 # order-1 model at H = 50: the QPs themselves are ill conditioned (cost-to-go entries ~1e10; two CPU runs of the reference
 # algorithm agree to 1e-6 over the closed loop): single steps are held to 1e-6, still 10x inside the north_star
 TF_TOL_BY_CONFIG = {'transmon_h50': 1e-6, 'transmon_h100': 1e-6}
@@ -43,6 +43,9 @@ CONFIGS = {
     'qubit': (lambda: systems.config_qubit(1), systems.ensemble_qubit, 4096),
     'transmon': (lambda: systems.config_transmon(1), systems.ensemble_transmon, 65536),
     'crosstalk': (lambda: systems.config_crosstalk(0.0), systems.ensemble_crosstalk, 65536),
+    # BASELINE config 3 at its longest horizon with the order-2 model: 8 members, closed loop AND teacher forcing
+    # (two CPU runs of the reference algorithm agree to 3e-10 over this closed loop)
+    'transmon_o2_h100': (lambda: systems.config_transmon(2, horizon=100, n_steps=20), systems.ensemble_transmon, 65536),
 }
 # teacher forcing only: the order-1 model at H = 50 (cost-to-go entries ~1e10, every step from the third on needs the ADMM
 # re-seeding of the working set): 16 members x 20 steps
